@@ -1,0 +1,93 @@
+// Device-resident scene layout (HBM).  Everything the reference keeps as two AoS arrays --
+// `singleobject` (164 B, raygpu/kernel.cu:48-74) and `bvh` (56 B, kernel.cu:79-96) -- re-laid for
+// 128-bit loads.  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include "dogeray_b200.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+// 64 B, 64 B-aligned binary node holding BOTH child boxes, so one visit decides both children.
+//   c0xy = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)
+//   c1xy = (c1.min.x, c1.max.x, c1.min.y, c1.max.y)
+//   cz   = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
+//   link = (child0, child1, 0, 0); child >= 0: node index, child < 0: leaf, ~child = primitive slot
+struct __align__(16) BvhNode {
+    float4 c0xy, c1xy, cz;
+    int4 link;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+// 48 B primitive, in tree (Morton) order.
+//   triangle: a = (v0, kind 0), b = (v1 - v0, 0), c = (v2 - v0, 0)   (edges precomputed in float,
+//             exactly the subtraction hit_tri does first, kernel.cu:287-288)
+//   sphere:   a = (centre, kind 1), b = (radius, 0, 0, 0)
+struct __align__(16) Prim {
+    float4 a, b, c;
+};
+static_assert(sizeof(Prim) == 48, "Prim must be 48 bytes");
+#define DRB_KIND_TRI 0
+#define DRB_KIND_SPHERE 1
+
+// 128 B shading record per primitive, same order as Prim; the first 48 B serve the common case.
+//   r0 = (face normal xyz, flags)                      flags: DRB_SF_*
+//   r1 = (col rgb, rough = addional.y)
+//   r2 = (addional.x, mat, texnum, rtexnum)            (ints stored as bits)
+//   r3 = (n1 xyz, t1.x)  r4 = (n2 xyz, t2.x)  r5 = (n3 xyz, t3.x)  r6 = (t1.y, t2.y, t3.y, 0)
+//   r7 = spare
+struct __align__(16) ShadeRec {
+    float4 r[8];
+};
+static_assert(sizeof(ShadeRec) == 128, "ShadeRec must be 128 bytes");
+#define DRB_SF_SPHERE 1u        // getnormal's type 0 branch, kernel.cu:707-710
+#define DRB_SF_FACE_NORMAL 2u   // norm.z != -20, kernel.cu:750
+#define DRB_SF_SMOOTH 4u        // face normal present && n1.z != -20 && smooth, kernel.cu:756
+#define DRB_SF_CHECKER 8u       // `tex` flag, kernel.cu:834
+#define DRB_SF_NEEDS_UV 16u     // barycentrics are needed (smooth, textured, checker)
+
+struct DevTexture {
+    const uchar4* texels;   // row-major, top-down
+    int32_t w, h;
+};
+
+struct LbvhDebug {              // integer outputs of the build, kept for drb_scene_lbvh
+    uint64_t* keys = nullptr;   // n, sorted
+    int32_t* order = nullptr;   // n
+    int32_t* parent = nullptr;  // n-1
+    int32_t* left = nullptr;    // n-1
+    int32_t* right = nullptr;   // n-1
+    float4* node_min = nullptr; // n-1
+    float4* node_max = nullptr; // n-1
+};
+
+struct drb_scene {
+    int device = 0;
+    drb_settings settings;
+    int64_t nobjects = 0;       // object lines
+    int64_t nprims = 0;         // renderable primitives (in the tree)
+    int64_t nnodes = 0;
+    BvhNode* nodes = nullptr;
+    Prim* prims = nullptr;
+    ShadeRec* recs = nullptr;
+    int32_t* orig_id = nullptr; // prim slot -> object line index
+    DevTexture* textures = nullptr;
+    int ntextures = 0;
+    std::vector<void*> texture_storage;
+    LbvhDebug dbg;
+    drb_build_info info;
+    cudaStream_t stream = nullptr;
+    // render work buffers, grown on demand (render.cu)
+    struct RenderBuffers* rb = nullptr;
+};
+
+#define DRB_CUDA(call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            drb_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__));   \
+            return DRB_ERR_CUDA;                                                                           \
+        }                                                                                                  \
+    } while (0)
+
+void drb_render_buffers_free(drb_scene* s);

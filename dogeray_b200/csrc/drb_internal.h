@@ -1,0 +1,30 @@
+// Internal declarations shared by the host-side translation units of libdogeray_b200.
+#pragma once
+#include "dogeray_b200.h"
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+struct drb_host_scene {
+    drb_settings settings;
+    std::vector<drb_object> objects;
+    std::vector<std::string> tex_paths;   // candidate texture files, sorted
+    int64_t skipped = 0;                  // lines that were not turned into objects
+    std::string first_warning;
+};
+
+// thread-local last-error string behind drb_last_error()
+void drb_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+void drb_clear_error();
+
+// texture name lookup of the reference (kernel.cu:1172-1183): first path whose lower-cased
+// text contains `query` (query itself is not lower-cased); -1 if none
+int drb_find_texture(const std::vector<std::string>& tex_paths, const std::string& query);
+std::vector<std::string> drb_scan_textures(const char* tex_dir);
+
+// decoded texture (RGBA8, alpha 0, rows top-down)
+struct drb_image {
+    int w = 0, h = 0;
+    std::vector<uint8_t> rgba;
+};
+int drb_load_ppm(const std::string& path, drb_image& out);

@@ -1,0 +1,914 @@
+// The wavefront path tracer.  Replaces `__global__ Kernel` and everything it calls
+// (raygpu/kernel.cu:244-333, 432-512, 640-691, 703-994, 998-1093) plus CudaStarter's launch
+// (kernel.cu:2562-2669) and the host accumulate loop (kernel.cu:2211-2218).
+//
+// The reference runs one thread per pixel through spp x depth x BVH nodes in a single megakernel.
+// Here a frame is cut into batches of (pixel, sample) paths and each batch runs as a wavefront:
+//
+//   k_generate   camera rays for every path slot of the batch                (kernel.cu:1016-1076)
+//   repeat max_depth times:
+//     k_trace    persistent warps pull 32 rays at a time from the ray queue, closest hit through the
+//                64 B two-box nodes with a per-thread stack, Moeller-Trumbore in the reference's
+//                operation order                                             (kernel.cu:468-512, 277-313)
+//     k_shade    normal / texture / material scatter or termination; survivors are appended to the
+//                next ray queue with one atomic per warp (ballot + popc)     (kernel.cu:787-982)
+//   k_resolve    per pixel, sum the batch's samples in sample order into the accumulator
+//
+// Terminated paths write their radiance to contrib[slot] exactly once, so the image is a
+// deterministic function of (scene, settings, seed) whatever order the queues end up in.
+//
+// This TU is compiled with -fmad=false: arithmetic rounds operation by operation like the
+// host-compiled reference; the box test asks for its FMAs explicitly.
+#include "drb_internal.h"
+#include "device_scene.cuh"
+#include "philox.cuh"
+#include "vec.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+constexpr int kStackSize = 96;          // >= kMaxTreeHeight in scene.cu
+constexpr uint32_t kInvalidPid = 0xFFFFFFFFu;
+constexpr float kTMax = 10000.0f;       // singlehit's mindist / aabb2's t_max, kernel.cu:246, 435
+constexpr float kEps = 0.0001f;         // hit_tri's EPSILON, kernel.cu:283
+
+struct Camera {
+    f3 from, llc, horizontal, vertical, uu, vu;
+    float lens_radius;
+    float wdiv, hdiv;                   // float(W / div), float(H / div), kernel.cu:1067-1068
+};
+
+struct FrameParams {
+    int W, H;                           // pixel grid traced
+    int tiles_x, tiles_y;               // 8x4 pixel tiles
+    uint32_t samples;                   // samples per pixel in this batch
+    uint32_t sample_base;               // global index of the batch's first sample
+    uint64_t seed;
+    int backtex;
+    float bg_intensity;
+    float scene_scale;                  // max |coordinate| of the scene bounds
+    Camera cam;
+};
+
+struct DevScene {
+    const BvhNode* nodes;
+    const Prim* prims;
+    const ShadeRec* recs;
+    const DevTexture* textures;
+    int nprims, ntextures;
+};
+
+// counters[]: 0,1 = ray queue sizes (ping-pong), 2 = trace ticket, 4..5 = 64-bit ray total
+enum { CNT_Q0 = 0, CNT_Q1 = 1, CNT_TICKET = 2, CNT_RAYS = 4, CNT_WORDS = 8 };
+
+struct Queues {
+    float4* ray_o[2];                   // (origin, pid bits)
+    float4* ray_d[2];                   // (direction, rng draw count bits)
+    float4* thr[2];                     // (attenuation rgb, 0)
+    uint2* hit;                         // (t bits, prim slot or -1)
+    float4* contrib;                    // radiance per path slot
+    uint32_t* counters;
+};
+
+// ---- path slot <-> pixel / sample ---------------------------------------------------------------
+// slot = ((tile * samples) + s) * 32 + lane, lane = (y & 3) * 8 + (x & 7): a warp is one 8x4 pixel
+// tile at one sample index (coherent camera rays), consecutive warps are consecutive samples of it.
+DRB_D bool slot_to_pixel(const FrameParams& fp, uint32_t slot, int& x, int& y, uint32_t& s)
+{
+    const uint32_t lane = slot & 31u, unit = slot >> 5;
+    s = unit % fp.samples;
+    const uint32_t tile = unit / fp.samples;
+    x = (int)(tile % (uint32_t)fp.tiles_x) * 8 + (int)(lane & 7u);
+    y = (int)(tile / (uint32_t)fp.tiles_x) * 4 + (int)(lane >> 3);
+    return x < fp.W && y < fp.H;
+}
+
+// ---- sampling helpers (kernel.cu:640-662, 988-994) ----------------------------------------------
+// The reference draws the components inside one make_float3(...) argument list, whose evaluation
+// order C++ leaves unspecified.  The oracle build (g++) evaluates it right to left, so the FIRST
+// draw of an attempt lands in the LAST component; the stream is consumed the same way here so that
+// paths stay aligned with the oracle draw for draw.  (Any order is the same distribution.)
+DRB_D f3 random_in_unit_sphere(PathRng& rng)
+{
+    for (;;) {
+        const float c = rng.uniform(), b = rng.uniform(), a = rng.uniform();
+        const f3 p = mk3(a * 2.0f - 1.0f, b * 2.0f - 1.0f, c * 2.0f - 1.0f);
+        const float l = length(p);
+        if (l * l >= 1.0f) continue;
+        return p;
+    }
+}
+DRB_D f3 random_in_unit_disk(PathRng& rng)
+{
+    for (;;) {
+        const float b = rng.uniform(), a = rng.uniform();
+        const f3 p = mk3(a * 2.0f - 1.0f, b * 2.0f - 1.0f, 0.0f);
+        const float l = length(p);
+        if (l * l >= 1.0f) continue;
+        return p;
+    }
+}
+
+// ---- k_generate ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(FrameParams fp, uint32_t nslots, Queues q)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    int x, y; uint32_t s;
+    if (!slot_to_pixel(fp, slot, x, y, s)) {
+        q.ray_o[0][slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalidPid));
+        q.ray_d[0][slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        q.thr[0][slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    PathRng rng;
+    rng.init(fp.seed, (uint32_t)x, (uint32_t)y, fp.sample_base + s, 0u);
+    const Camera& c = fp.cam;
+    // kernel.cu:1067-1068: float(x) + double uniform, divided by float(W/div), rounded to float
+    const double u1 = (double)rng.uniform();
+    const float nu = (float)(((double)(float)x + u1) / (double)c.wdiv);
+    const double u2 = (double)rng.uniform();
+    const float nv = (float)(((double)(float)y + u2) / (double)c.hdiv);
+    const f3 rd = mk3(c.lens_radius) * random_in_unit_disk(rng);
+    const f3 offset = c.uu * mk3(rd.x) + c.vu * mk3(rd.y);
+    const f3 dir = c.llc + mk3(nu) * c.horizontal + mk3(nv) * c.vertical - c.from - offset;
+    const f3 org = c.from + offset;
+    q.ray_o[0][slot] = make_float4(org.x, org.y, org.z, __uint_as_float(slot));
+    q.ray_d[0][slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(rng.draws));
+    q.thr[0][slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+}
+
+// ---- closest hit ----------------------------------------------------------------------------------
+DRB_D float safe_inv(float d)
+{
+    // aabb2 divides by the direction component (kernel.cu:252); a zero component behaves like a
+    // vanishing one here, which keeps the slab arithmetic free of inf - inf
+    const float lim = 1.0e-20f;
+    if (fabsf(d) < lim) d = copysignf(lim, d);
+    return 1.0f / d;
+}
+
+// hit_tri (kernel.cu:277-313) on precomputed edges; updates (best, bestp) under the acceptance rules
+// of singlehit / hit (kernel.cu:449, 488): EPS < t < 10000 and t < best
+DRB_D void intersect_prim(const Prim* __restrict__ prims, int slot, const f3& o, const f3& d, float& best, int& bestp)
+{
+    const float4 pa = __ldg(&prims[slot].a);
+    const float4 pb = __ldg(&prims[slot].b);
+    if (__float_as_int(pa.w) == DRB_KIND_TRI) {
+        const float4 pc = __ldg(&prims[slot].c);
+        const f3 v0 = xyz(pa), e1 = xyz(pb), e2 = xyz(pc);
+        const f3 h = cross(d, e2);
+        const float a = dot(e1, h);
+        if (a > -kEps && a < kEps) return;
+        const float f = 1.0f / a;
+        const f3 sv = o - v0;
+        const float u = f * dot(sv, h);
+        if (u < 0.0f || u > 1.0f) return;
+        const f3 qv = cross(sv, e1);
+        const float v = f * dot(d, qv);
+        if (v < 0.0f || u + v > 1.0f) return;
+        const float t = f * dot(e2, qv);
+        if (t > kEps && t < best) { best = t; bestp = slot; }
+    } else {
+        // hit_sphere (kernel.cu:316-333): near root only
+        const f3 oc = o - xyz(pa);
+        const float radius = pb.x;
+        const float ld = length(d), lo = length(oc);
+        const float a = ld * ld;
+        const float half_b = dot(oc, d);
+        const float c = lo * lo - radius * radius;
+        const float disc = half_b * half_b - a * c;
+        if (disc < 0.0f) return;
+        const float t = (-half_b - sqrtf(disc)) / a;
+        if (t > 0.0f && t < best) { best = t; bestp = slot; }
+    }
+}
+
+DRB_D void trace_closest(const DevScene& sc, float scene_scale, const f3& o, const f3& d, float& best, int& bestp)
+{
+    best = kTMax; bestp = -1;
+    if (sc.nprims == 0) return;
+    const float ix = safe_inv(d.x), iy = safe_inv(d.y), iz = safe_inv(d.z);
+    // per-ray slab padding: boxes are stored tight; the ray sees them grown by a few ulps of the
+    // distances involved, so a hit the triangle test accepts by rounding is never culled by a box
+    const float pad = (fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + scene_scale) * 1.9073486e-6f;
+    const float oxl = (o.x + pad) * ix, oxh = (o.x - pad) * ix;
+    const float oyl = (o.y + pad) * iy, oyh = (o.y - pad) * iy;
+    const float ozl = (o.z + pad) * iz, ozh = (o.z - pad) * iz;
+    int stack[kStackSize];
+    int sp = 0;
+    int node = 0;
+    for (;;) {
+        if (node >= 0) {
+            const BvhNode* np = sc.nodes + node;
+            const float4 n0 = __ldg(&np->c0xy), n1 = __ldg(&np->c1xy), nz = __ldg(&np->cz);
+            const int4 link = __ldg(&np->link);
+            float a, b;
+            a = fmaf(n0.x, ix, -oxl); b = fmaf(n0.y, ix, -oxh);
+            float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
+            a = fmaf(n0.z, iy, -oyl); b = fmaf(n0.w, iy, -oyh);
+            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+            a = fmaf(nz.x, iz, -ozl); b = fmaf(nz.y, iz, -ozh);
+            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
+            a = fmaf(n1.x, ix, -oxl); b = fmaf(n1.y, ix, -oxh);
+            float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
+            a = fmaf(n1.z, iy, -oyl); b = fmaf(n1.w, iy, -oyh);
+            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+            a = fmaf(nz.z, iz, -ozl); b = fmaf(nz.w, iz, -ozh);
+            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
+            const bool h0 = fmaxf(tn0, 0.0f) <= fminf(tf0, best);
+            const bool h1 = fmaxf(tn1, 0.0f) <= fminf(tf1, best);
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;
+                stack[sp++] = swap ? link.x : link.y;
+                node = swap ? link.y : link.x;
+                continue;
+            }
+            if (h0) { node = link.x; continue; }
+            if (h1) { node = link.y; continue; }
+        } else {
+            intersect_prim(sc.prims, ~node, o, d, best, bestp);
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+}
+
+// persistent warps: each warp claims 32 consecutive rays per ticket
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Queues q, int cur)
+{
+    const uint32_t count = q.counters[cur];
+    const float4* __restrict__ ro = q.ray_o[cur];
+    const float4* __restrict__ rdv = q.ray_d[cur];
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&q.counters[CNT_TICKET], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const uint32_t i = base + lane;
+        if (i < count) {
+            const float4 o4 = ro[i], d4 = rdv[i];
+            float t = -1.0f; int p = -1;
+            if (__float_as_uint(o4.w) != kInvalidPid) {
+                float best; int bestp;
+                trace_closest(sc, scene_scale, xyz(o4), xyz(d4), best, bestp);
+                if (bestp >= 0) { t = best; p = bestp; }
+            }
+            q.hit[i] = make_uint2(__float_as_uint(t), (uint32_t)p);
+        }
+    }
+}
+
+// ---- shading ---------------------------------------------------------------------------------------
+// tex2D<uchar4> with the reference's descriptor (kernel.cu:1959-1964): normalised coordinates, wrap,
+// point filter; rows top-down
+DRB_D uchar4 tex_fetch(const DevTexture* __restrict__ table, int ntex, int k, float u, float v)
+{
+    uchar4 r = make_uchar4(0, 0, 0, 0);
+    if (k < 0 || k >= ntex) return r;
+    const DevTexture t = table[k];
+    if (t.w <= 0 || t.h <= 0 || t.texels == nullptr) return r;
+    const float fu = u - floorf(u), fv = v - floorf(v);
+    int ix = (int)floorf(fu * (float)t.w), iy = (int)floorf(fv * (float)t.h);
+    if (!(ix >= 0)) ix = 0;
+    if (!(iy >= 0)) iy = 0;
+    if (ix >= t.w) ix = t.w - 1;
+    if (iy >= t.h) iy = t.h - 1;
+    return __ldg(&t.texels[(size_t)iy * (size_t)t.w + (size_t)ix]);
+}
+
+DRB_D f3 reflect(f3 v, f3 n)
+{
+    const float k = 2.0f * dot(v, n);               // 2.0 * dot in double is the same float (kernel.cu:668)
+    return v - mk3(k) * n;
+}
+
+DRB_D float reflectance(float cosine, float ref_idx)
+{
+    // Schlick, kernel.cu:686-691; the (1 - cosine)^5 term is evaluated in double there
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    const double x = (double)(1.0f - cosine);
+    const double x2 = x * x;
+    return (float)((double)r0 + (double)(1.0f - r0) * (x2 * x2 * x));
+}
+
+DRB_D f3 refract(f3 uv, f3 n, float etai_over_etat)
+{
+    // kernel.cu:678-683
+    const float cos_theta = fminf(dot(uv * mk3(-1.0f), n), 1.0f);
+    const f3 perp = mk3(etai_over_etat) * (uv + mk3(cos_theta) * n);
+    const float lp = length(perp);
+    const float k = (float)(-sqrt(fabs(1.0 - (double)(lp * lp))));
+    return perp + mk3(k) * n;
+}
+
+// environment colour, kernel.cu:951-976 (the caller applies attenuation and intensity in the reference's order)
+DRB_D f3 environment(const DevScene& sc, const FrameParams& fp, f3 raydir)
+{
+    const f3 ud = normalize(raydir);
+    if (fp.backtex > -1) {
+        const double dx = (double)ud.x, dy = (double)ud.y, dz = (double)ud.z + 1.0;
+        const float m = (float)(2.0 * sqrt(dx * dx + dy * dy + dz * dz));
+        f3 t = ud / mk3(m) + mk3(0.5f);
+        t.y = -t.y;
+        const uchar4 c = tex_fetch(sc.textures, sc.ntextures, fp.backtex, t.x, -t.y + 1.0f);
+        return mk3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f);
+    }
+    const float t = (float)(0.5 * ((double)ud.y + 1.0));
+    const float omt = (float)(1.0 - (double)t);
+    return mk3(omt) * mk3(1.0f) + mk3(t) * mk3(0.5f, 0.7f, 1.0f);
+}
+
+__global__ void __launch_bounds__(256) k_shade(DevScene sc, FrameParams fp, Queues q, int cur, int last_bounce)
+{
+    const uint32_t count = q.counters[cur];
+    const int nxt = cur ^ 1;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // whole warps iterate together so the ballot below is well defined
+    const uint32_t rounded = (count + 31u) & ~31u;
+    uint64_t local_rays = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+        bool alive = false;
+        float4 no, nd, nt;
+        if (i < count) {
+            const float4 o4 = q.ray_o[cur][i];
+            const uint32_t pid = __float_as_uint(o4.w);
+            if (pid != kInvalidPid) {
+                local_rays++;
+                const float4 d4 = q.ray_d[cur][i];
+                const float4 a4 = q.thr[cur][i];
+                const uint2 h = q.hit[i];
+                const f3 rayo = xyz(o4), raydir = xyz(d4);
+                f3 atten = xyz(a4);
+                const float t = __uint_as_float(h.x);
+                const int prim = (int)h.y;
+                if (!(prim >= 0 && t > 0.0f)) {
+                    const f3 c = atten * environment(sc, fp, raydir) * mk3(fp.bg_intensity);
+                    q.contrib[pid] = make_float4(c.x, c.y, c.z, 0.f);
+                } else {
+                    const ShadeRec* rec = sc.recs + prim;
+                    const float4 r0 = __ldg(&rec->r[0]), r1 = __ldg(&rec->r[1]), r2 = __ldg(&rec->r[2]);
+                    const uint32_t flags = __float_as_uint(r0.w);
+                    const int mat = __float_as_int(r2.y), texnum = __float_as_int(r2.z), rtexnum = __float_as_int(r2.w);
+                    const f3 hitpoint = rayo + mk3(t) * raydir;
+                    f3 N; f3 texco = mk3(0.f);
+                    if (flags & DRB_SF_SPHERE) {
+                        const float4 pa = __ldg(&sc.prims[prim].a), pb = __ldg(&sc.prims[prim].b);
+                        N = (hitpoint - xyz(pa)) / mk3(pb.x);                // kernel.cu:708, not normalised
+                    } else {
+                        // getnormal, kernel.cu:713-767
+                        if ((flags & DRB_SF_NEEDS_UV) || !(flags & DRB_SF_FACE_NORMAL)) {
+                            const float4 pa = __ldg(&sc.prims[prim].a), pb = __ldg(&sc.prims[prim].b), pc = __ldg(&sc.prims[prim].c);
+                            const f3 v0 = xyz(pa), e1 = xyz(pb), e2 = xyz(pc);
+                            N = cross(e1, e2);
+                            if (flags & DRB_SF_NEEDS_UV) {
+                                const f3 pvec = cross(raydir, e2);
+                                const float det = dot(e1, pvec);
+                                const float inv_det = 1.0f / det;
+                                const f3 tvec = rayo - v0;
+                                const float bu = dot(tvec, pvec) * inv_det;
+                                const f3 qvec = cross(tvec, e1);
+                                const float bv = dot(raydir, qvec) * inv_det;
+                                const float bw = 1.0f - bu - bv;
+                                const float4 r3 = __ldg(&rec->r[3]), r4 = __ldg(&rec->r[4]), r5 = __ldg(&rec->r[5]), r6 = __ldg(&rec->r[6]);
+                                texco = mk3(bw) * mk3(r3.w, r6.x, 0.f) + mk3(bu) * mk3(r4.w, r6.y, 0.f) + mk3(bv) * mk3(r5.w, r6.z, 0.f);
+                                if (flags & DRB_SF_SMOOTH) N = mk3(bw) * xyz(r3) + mk3(bu) * xyz(r4) + mk3(bv) * xyz(r5);
+                                else if (flags & DRB_SF_FACE_NORMAL) N = xyz(r0);
+                            }
+                        } else {
+                            N = xyz(r0);
+                        }
+                        N = normalize(N);
+                    }
+                    const bool front = dot(raydir, N) < 0.0f;                  // get_face_normal, kernel.cu:235-238
+                    if (!front) N = N * mk3(-1.0f);
+
+                    f3 ocolor = xyz(r1);
+                    float rough = r1.w;
+                    if (texnum >= 0) {
+                        const uchar4 c = tex_fetch(sc.textures, sc.ntextures, texnum, texco.x, -texco.y + 1.0f);
+                        ocolor = mk3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f);
+                    } else if (flags & DRB_SF_CHECKER) {
+                        // checker, kernel.cu:776-784
+                        const float yes = floorf(texco.x * 10.0f) + floorf(texco.y * 10.0f);
+                        if (fmodf(yes, 2.0f) == 0.0f) ocolor = mk3(0.8f);
+                    }
+                    if (rtexnum >= 0) {
+                        const uchar4 c = tex_fetch(sc.textures, sc.ntextures, rtexnum, texco.x, -texco.y + 1.0f);
+                        rough = (float)c.x / 255.0f / 2.0f;
+                    }
+
+                    int x, y; uint32_t s;
+                    slot_to_pixel(fp, pid, x, y, s);
+                    PathRng rng;
+                    rng.init(fp.seed, (uint32_t)x, (uint32_t)y, fp.sample_base + s, __float_as_uint(d4.w));
+
+                    f3 ndir = raydir;
+                    alive = true;
+                    if (mat == 0) {
+                        // diffuse, kernel.cu:848-866
+                        f3 target = hitpoint + N;
+                        if (r2.x == 0.0f) target = target + random_in_unit_sphere(rng);
+                        else target = target + normalize(random_in_unit_sphere(rng));
+                        atten = atten * ocolor;
+                        ndir = normalize(target - hitpoint);
+                    } else if (mat == 2) {
+                        atten = atten * ocolor;                                 // mirror, kernel.cu:867-874
+                        ndir = reflect(normalize(raydir), N);
+                    } else if (mat == 3) {
+                        const f3 reflected = reflect(normalize(raydir), N);     // metal, kernel.cu:875-883
+                        atten = atten * ocolor;
+                        ndir = reflected + mk3(rough) * random_in_unit_sphere(rng);
+                    } else if (mat == 5) {
+                        const float pick = rng.uniform();                       // glossy, kernel.cu:884-912
+                        if (pick > 0.8f) {
+                            const f3 reflected = reflect(normalize(raydir), N);
+                            atten = atten * ocolor;
+                            ndir = reflected + mk3(rough) * random_in_unit_sphere(rng);
+                        } else {
+                            f3 target = hitpoint + N;
+                            target = target + random_in_unit_sphere(rng);
+                            atten = atten * ocolor;
+                            ndir = normalize(target - hitpoint);
+                        }
+                    } else if (mat == 4) {
+                        // glass, kernel.cu:914-939 (ior comes from addional.y even when a roughness map is bound)
+                        const float ir = r1.w;
+                        const float ratio = front ? (float)(1.0 / (double)ir) : ir;
+                        const f3 unit = normalize(raydir);
+                        const float cos_theta = fminf(dot(unit * mk3(-1.0f), N), 1.0f);
+                        const float sin_theta = (float)sqrt(1.0 - (double)(cos_theta * cos_theta));
+                        const bool cannot_refract = (ratio * sin_theta) > 1.0f;
+                        if (cannot_refract || reflectance(cos_theta, ratio) > rng.uniform()) ndir = reflect(unit, N);
+                        else ndir = refract(unit, N, ratio);
+                        atten = atten * ocolor;
+                    } else {
+                        const f3 c = ocolor * atten;                            // emissive, kernel.cu:941-944
+                        q.contrib[pid] = make_float4(c.x, c.y, c.z, 0.f);
+                        alive = false;
+                    }
+                    if (alive && last_bounce) alive = false;                    // depth exhausted: black, kernel.cu:981
+                    if (alive) {
+                        no = make_float4(hitpoint.x, hitpoint.y, hitpoint.z, o4.w);
+                        nd = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(rng.draws));
+                        nt = make_float4(atten.x, atten.y, atten.z, 0.f);
+                    }
+                }
+            }
+        }
+        // warp-aggregated append: one atomic per warp, order inside the warp preserved
+        const unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (mask) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(mask) - 1)) base = atomicAdd(&q.counters[nxt], (uint32_t)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+            if (alive) {
+                const uint32_t dst = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                q.ray_o[nxt][dst] = no;
+                q.ray_d[nxt][dst] = nd;
+                q.thr[nxt][dst] = nt;
+            }
+        }
+    }
+    // ray statistics: one 64-bit atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) local_rays += __shfl_xor_sync(0xffffffffu, local_rays, off);
+    if (lane == 0 && local_rays) atomicAdd(reinterpret_cast<unsigned long long*>(&q.counters[CNT_RAYS]), (unsigned long long)local_rays);
+}
+
+// counters for the next bounce: clear the queue that k_shade is about to fill and the trace ticket
+__global__ void k_prepare(uint32_t* counters, int clear_queue, int set_queue, uint32_t set_value)
+{
+    if (threadIdx.x == 0) {
+        if (clear_queue >= 0) counters[clear_queue] = 0u;
+        if (set_queue >= 0) counters[set_queue] = set_value;
+        counters[CNT_TICKET] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_resolve(FrameParams fp, const float4* __restrict__ contrib, float* __restrict__ accum, int accumulate)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= fp.W || y >= fp.H) return;
+    const uint32_t tile = (uint32_t)(y >> 2) * (uint32_t)fp.tiles_x + (uint32_t)(x >> 3);
+    const uint32_t lane = (uint32_t)((y & 3) * 8 + (x & 7));
+    f3 sum = mk3(0.f);
+    for (uint32_t s = 0; s < fp.samples; ++s) {
+        const float4 c = contrib[(size_t)(tile * fp.samples + s) * 32u + lane];
+        sum = sum + mk3(c.x, c.y, c.z);                              // ColorOutput += raycolor(...), kernel.cu:1076
+    }
+    float* dst = accum + ((size_t)y * fp.W + x) * 3;
+    if (accumulate) { dst[0] += sum.x; dst[1] += sum.y; dst[2] += sum.z; }
+    else { dst[0] = sum.x; dst[1] = sum.y; dst[2] = sum.z; }
+}
+
+// rays of explicit (o, d) arrays -> queue 0
+__global__ void k_load_rays(const float* __restrict__ o3, const float* __restrict__ d3, uint32_t n, Queues q)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q.ray_o[0][i] = make_float4(o3[3*i], o3[3*i+1], o3[3*i+2], __uint_as_float(i));
+    q.ray_d[0][i] = make_float4(d3[3*i], d3[3*i+1], d3[3*i+2], 0.f);
+}
+__global__ void k_store_ids(const uint2* __restrict__ hit, const int32_t* __restrict__ orig, uint32_t n, int32_t* __restrict__ ids, float* __restrict__ t)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 h = hit[i];
+    const int p = (int)h.y;
+    ids[i] = p >= 0 ? orig[p] : -1;
+    t[i] = __uint_as_float(h.x);
+}
+// camera rays of queue 0 (slot order) -> row-major arrays
+__global__ void k_store_rays(FrameParams fp, uint32_t nslots, Queues q, float* __restrict__ o3, float* __restrict__ d3)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    int x, y; uint32_t s;
+    if (!slot_to_pixel(fp, slot, x, y, s)) return;
+    const float4 o = q.ray_o[0][slot], d = q.ray_d[0][slot];
+    const size_t k = ((size_t)y * fp.W + x) * 3;
+    o3[k] = o.x; o3[k+1] = o.y; o3[k+2] = o.z;
+    d3[k] = d.x; d3[k+1] = d.y; d3[k+2] = d.z;
+}
+
+__global__ void k_tonemap(const float* __restrict__ accum, size_t n, float scale, uint8_t* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = accum[i] * 255.0f * scale;
+    const int qv = (v != v) ? 0 : (v >= 255.0f ? 255 : (v <= 0.0f ? 0 : (int)v));
+    out[i] = (uint8_t)qv;
+}
+
+// Kernel's integer output (kernel.cu:1083-1085) from a float sum: out[x*H + y] = trunc(sum * 255 * (1/spp))
+__global__ void k_frame_i3(const float* __restrict__ accum, int w, int h, int full_h, float scale, int32_t* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float* src = accum + ((size_t)y * w + x) * 3;
+    int32_t* dst = out + ((size_t)x * full_h + y) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v = src[c] * 255.0f * scale;
+        dst[c] = (v != v) ? 0 : (v >= 2147483648.0f ? INT32_MAX : (v <= -2147483648.0f ? INT32_MIN : (int32_t)v));
+    }
+}
+
+} // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------
+struct RenderBuffers {
+    size_t capacity = 0;                // path slots
+    Queues q{};
+    int trace_blocks = 0, shade_blocks = 0;
+};
+
+namespace {
+
+// Camera basis exactly as Kernel derives it per thread (kernel.cu:1016-1052), once on the host.
+Camera make_camera(const drb_settings& st, int W, int H, int divisor)
+{
+    auto n3 = [](float x, float y, float z, float out[3]) {
+        const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+        out[0] = x * inv; out[1] = y * inv; out[2] = z * inv;
+    };
+    const float div = (float)divisor;
+    Camera c;
+    c.wdiv = (float)((float)W / div);
+    c.hdiv = (float)((float)H / div);
+    const float aspect = c.wdiv / c.hdiv;
+    const float fov = (float)((double)(float)st.fov * M_PI / 180);
+    const float vh = (float)(2.0 * (double)tanf(fov / 2));
+    const float vw = aspect * vh;
+    float wu[3], uu[3], vu[3];
+    n3(st.cam[0] - st.look[0], st.cam[1] - st.look[1], st.cam[2] - st.look[2], wu);
+    // cross(vup, wu), vup = (0,1,0)
+    const float cx = 1.0f * wu[2] - 0.0f * wu[1], cy = 0.0f * wu[0] - 0.0f * wu[2], cz = 0.0f * wu[1] - 1.0f * wu[0];
+    n3(cx, cy, cz, uu);
+    vu[0] = wu[1] * uu[2] - wu[2] * uu[1];
+    vu[1] = wu[2] * uu[0] - wu[0] * uu[2];
+    vu[2] = wu[0] * uu[1] - wu[1] * uu[0];
+    float hor[3], ver[3], llc[3];
+    for (int a = 0; a < 3; ++a) {
+        hor[a] = (st.focus * vw) * uu[a];
+        ver[a] = (st.focus * vh) * vu[a];
+    }
+    for (int a = 0; a < 3; ++a) llc[a] = ((st.cam[a] - hor[a] / 2.0f) - ver[a] / 2.0f) - st.focus * wu[a];
+    c.from = f3{ st.cam[0], st.cam[1], st.cam[2] };
+    c.llc = f3{ llc[0], llc[1], llc[2] };
+    c.horizontal = f3{ hor[0], hor[1], hor[2] };
+    c.vertical = f3{ ver[0], ver[1], ver[2] };
+    c.uu = f3{ uu[0], uu[1], uu[2] };
+    c.vu = f3{ vu[0], vu[1], vu[2] };
+    c.lens_radius = st.aperture / 2;
+    return c;
+}
+
+int ensure_buffers(drb_scene* s, size_t slots)
+{
+    if (!s->rb) s->rb = new RenderBuffers();
+    RenderBuffers* rb = s->rb;
+    if (rb->capacity >= slots && rb->q.counters) return DRB_OK;
+    drb_render_buffers_free(s);
+    s->rb = rb = new RenderBuffers();
+    Queues& q = rb->q;
+    for (int k = 0; k < 2; ++k) {
+        DRB_CUDA(cudaMalloc((void**)&q.ray_o[k], slots * sizeof(float4)));
+        DRB_CUDA(cudaMalloc((void**)&q.ray_d[k], slots * sizeof(float4)));
+        DRB_CUDA(cudaMalloc((void**)&q.thr[k], slots * sizeof(float4)));
+    }
+    DRB_CUDA(cudaMalloc((void**)&q.hit, slots * sizeof(uint2)));
+    DRB_CUDA(cudaMalloc((void**)&q.contrib, slots * sizeof(float4)));
+    DRB_CUDA(cudaMalloc((void**)&q.counters, CNT_WORDS * sizeof(uint32_t)));
+    DRB_CUDA(cudaMemset(q.counters, 0, CNT_WORDS * sizeof(uint32_t)));
+    rb->capacity = slots;
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, 128, 0));
+    rb->trace_blocks = sms * std::max(per_sm, 1);
+    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 256, 0));
+    rb->shade_blocks = sms * std::max(per_sm, 1);
+    return DRB_OK;
+}
+
+DevScene dev_scene(const drb_scene* s)
+{
+    DevScene d;
+    d.nodes = s->nodes; d.prims = s->prims; d.recs = s->recs; d.textures = s->textures;
+    d.nprims = (int)s->nprims; d.ntextures = s->ntextures;
+    return d;
+}
+
+float scene_scale(const drb_scene* s)
+{
+    float m = 0.f;
+    for (int a = 0; a < 3; ++a) m = std::max(m, std::max(fabsf(s->info.bounds_min[a]), fabsf(s->info.bounds_max[a])));
+    return s->nprims ? m : 0.f;
+}
+
+int check_settings(const drb_settings* st)
+{
+    if (!st) { drb_set_error("null settings"); return DRB_ERR_ARG; }
+    if (st->width <= 0 || st->height <= 0 || st->width > 32768 || st->height > 32768) { drb_set_error("bad image size %dx%d", st->width, st->height); return DRB_ERR_ARG; }
+    if (st->max_depth < 0) { drb_set_error("bad max_depth %d", st->max_depth); return DRB_ERR_ARG; }
+    return DRB_OK;
+}
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
+    cudaEvent_t get() { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); return e; }
+};
+
+// the wavefront loop for a W x H grid; accum is a device buffer of W*H*3 floats
+int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int W, int H, int divisor, float* accum, drb_stats* stats)
+{
+    drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
+    const uint32_t total_samples = o.sample_count ? o.sample_count : (uint32_t)std::max(st->spp, 0);
+    cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
+    DRB_CUDA(cudaSetDevice(s->device));
+    if (st->backtex >= s->ntextures) { drb_set_error("settings.backtex %d out of range (scene has %d textures)", st->backtex, s->ntextures); return DRB_ERR_ARG; }
+
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
+    const size_t slots_per_sample = (size_t)tiles_x * tiles_y * 32;
+    size_t want = o.batch_paths ? o.batch_paths : (size_t)(16u << 20);
+    uint32_t per_batch = (uint32_t)std::max<size_t>(1, want / slots_per_sample);
+    per_batch = std::min<uint32_t>(per_batch, std::max<uint32_t>(total_samples, 1u));
+    if (slots_per_sample * per_batch >= 0xFFFFFFF0ull) { drb_set_error("batch too large"); return DRB_ERR_ARG; }
+    if (int rc = ensure_buffers(s, slots_per_sample * per_batch)) return rc;
+    RenderBuffers* rb = s->rb;
+    Queues q = rb->q;
+
+    FrameParams fp;
+    fp.W = W; fp.H = H; fp.tiles_x = tiles_x; fp.tiles_y = tiles_y;
+    fp.seed = o.seed; fp.backtex = st->backtex; fp.bg_intensity = st->bg_intensity;
+    fp.scene_scale = scene_scale(s);
+    fp.cam = make_camera(*st, st->width, st->height, divisor);     // aspect and u/v denominators come from the FULL size
+    const DevScene sc = dev_scene(s);
+
+    EventPool pool;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_ev;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (stats) {
+        ev_begin = pool.get(); ev_end = pool.get();
+        DRB_CUDA(cudaMemsetAsync(q.counters + CNT_RAYS, 0, 8, stream));
+        DRB_CUDA(cudaEventRecord(ev_begin, stream));
+    }
+    uint32_t launches = 0, trace_launches = 0;
+    const bool accumulate_first = (o.flags & DRB_FLAG_ACCUMULATE) != 0;
+    if (total_samples == 0 && !accumulate_first) DRB_CUDA(cudaMemsetAsync(accum, 0, (size_t)W * H * 3 * sizeof(float), stream));
+
+    for (uint32_t done = 0; done < total_samples; done += per_batch) {
+        fp.samples = std::min(per_batch, total_samples - done);
+        fp.sample_base = o.sample_base + done;
+        const uint32_t nslots = (uint32_t)(slots_per_sample * fp.samples);
+        DRB_CUDA(cudaMemsetAsync(q.contrib, 0, (size_t)nslots * sizeof(float4), stream));
+        k_generate<<<(nslots + 255) / 256, 256, 0, stream>>>(fp, nslots, q);
+        k_prepare<<<1, 32, 0, stream>>>(q.counters, 1, 0, nslots);
+        launches += 2;
+        int cur = 0;
+        for (int b = 0; b < st->max_depth; ++b) {
+            if (stats) { auto e0 = pool.get(), e1 = pool.get(); trace_ev.push_back({ e0, e1 }); DRB_CUDA(cudaEventRecord(e0, stream)); }
+            k_trace<<<rb->trace_blocks, 128, 0, stream>>>(sc, fp.scene_scale, q, cur);
+            if (stats) DRB_CUDA(cudaEventRecord(trace_ev.back().second, stream));
+            k_shade<<<rb->shade_blocks, 256, 0, stream>>>(sc, fp, q, cur, b == st->max_depth - 1 ? 1 : 0);
+            k_prepare<<<1, 32, 0, stream>>>(q.counters, cur, -1, 0u);
+            launches += 3; trace_launches += 1;
+            cur ^= 1;
+        }
+        dim3 rb_block(32, 8), rb_grid((W + 31) / 32, (H + 7) / 8);
+        k_resolve<<<rb_grid, rb_block, 0, stream>>>(fp, q.contrib, accum, (accumulate_first || done > 0) ? 1 : 0);
+        launches += 1;
+    }
+    DRB_CUDA(cudaGetLastError());
+    if (stats) {
+        DRB_CUDA(cudaEventRecord(ev_end, stream));
+        uint64_t rays = 0;
+        DRB_CUDA(cudaMemcpyAsync(&rays, q.counters + CNT_RAYS, 8, cudaMemcpyDeviceToHost, stream));
+        DRB_CUDA(cudaStreamSynchronize(stream));
+        memset(stats, 0, sizeof *stats);
+        stats->paths = (uint64_t)W * H * total_samples;
+        stats->rays = rays;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end); stats->total_ms = ms;
+        double tms = 0;
+        for (auto& pr : trace_ev) { cudaEventElapsedTime(&ms, pr.first, pr.second); tms += ms; }
+        stats->trace_ms = (float)tms;
+        stats->trace_launches = trace_launches;
+        stats->kernel_launches = launches;
+    }
+    return DRB_OK;
+}
+
+} // namespace
+
+void drb_render_buffers_free(drb_scene* s)
+{
+    if (!s || !s->rb) return;
+    Queues& q = s->rb->q;
+    for (int k = 0; k < 2; ++k) { cudaFree(q.ray_o[k]); cudaFree(q.ray_d[k]); cudaFree(q.thr[k]); }
+    cudaFree(q.hit); cudaFree(q.contrib); cudaFree(q.counters);
+    delete s->rb;
+    s->rb = nullptr;
+}
+
+extern "C" {
+
+void drb_opts_default(drb_opts* o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+}
+
+int drb_render_device(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_dev, drb_stats* stats)
+{
+    if (!s || !accum_dev) { drb_set_error("drb_render_device: null argument"); return DRB_ERR_ARG; }
+    if (int rc = check_settings(settings)) return rc;
+    return render_core(s, settings, opts, settings->width, settings->height, 1, accum_dev, stats);
+}
+
+int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats)
+{
+    if (!s || !accum_host) { drb_set_error("drb_render: null argument"); return DRB_ERR_ARG; }
+    if (int rc = check_settings(settings)) return rc;
+    DRB_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)settings->width * settings->height * 3;
+    float* d = nullptr;
+    DRB_CUDA(cudaMalloc((void**)&d, n * sizeof(float)));
+    drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
+    cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
+    int rc = DRB_OK;
+    if (o.flags & DRB_FLAG_ACCUMULATE) {
+        if (cudaMemcpyAsync(d, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DRB_ERR_CUDA;
+    }
+    if (rc == DRB_OK) rc = render_core(s, settings, &o, settings->width, settings->height, 1, d, stats);
+    if (rc == DRB_OK) {
+        cudaError_t e = cudaMemcpyAsync(accum_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { drb_set_error("download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opts, int divisor, int32_t* out)
+{
+    if (!s || !out || divisor < 1) { drb_set_error("drb_frame_i3: bad argument"); return DRB_ERR_ARG; }
+    if (int rc = check_settings(settings)) return rc;
+    DRB_CUDA(cudaSetDevice(s->device));
+    // the grid CudaStarter launches: (W/div/8) x (H/div/8) blocks of 8x8 (kernel.cu:2634-2636)
+    const int W = settings->width / divisor / 8 * 8, H = settings->height / divisor / 8 * 8;
+    if (W <= 0 || H <= 0) return DRB_OK;
+    drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
+    o.flags &= ~DRB_FLAG_ACCUMULATE;
+    cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
+    const uint32_t spp = o.sample_count ? o.sample_count : (uint32_t)std::max(settings->spp, 0);
+    float* d_acc = nullptr; int32_t* d_out = nullptr;
+    const size_t nfull = (size_t)settings->width * settings->height * 3;
+    DRB_CUDA(cudaMalloc((void**)&d_acc, (size_t)W * H * 3 * sizeof(float)));
+    if (cudaMalloc((void**)&d_out, nfull * sizeof(int32_t)) != cudaSuccess) { cudaFree(d_acc); drb_set_error("out of device memory"); return DRB_ERR_NOMEM; }
+    int rc = DRB_OK;
+    {
+        // entries outside the launched grid stay as the caller left them
+        cudaError_t e = cudaMemcpyAsync(d_out, out, nfull * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) { drb_set_error("upload failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
+    }
+    if (rc == DRB_OK) rc = render_core(s, settings, &o, W, H, divisor, d_acc, nullptr);
+    if (rc == DRB_OK) {
+        const float scale = (float)(1.0 / (double)(float)spp);          // kernel.cu:1081
+        dim3 block(8, 8), grid(W / 8, H / 8);
+        k_frame_i3<<<grid, block, 0, stream>>>(d_acc, W, H, settings->height, scale, d_out);
+        cudaError_t e = cudaMemcpyAsync(out, d_out, nfull * sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { drb_set_error("frame download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
+    }
+    cudaFree(d_acc); cudaFree(d_out);
+    return rc;
+}
+
+int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int32_t* ids, float* t)
+{
+    if (!s || n < 0 || (n && (!o3 || !d3 || !ids))) { drb_set_error("drb_trace_ids: bad argument"); return DRB_ERR_ARG; }
+    if (n == 0) return DRB_OK;
+    if (n >= 0x7FFFFFF0ll) { drb_set_error("too many rays"); return DRB_ERR_ARG; }
+    DRB_CUDA(cudaSetDevice(s->device));
+    if (int rc = ensure_buffers(s, (size_t)n)) return rc;
+    RenderBuffers* rb = s->rb;
+    Queues q = rb->q;
+    cudaStream_t stream = s->stream;
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int32_t* d_ids = nullptr;
+    DRB_CUDA(cudaMalloc((void**)&d_o, (size_t)n * 12));
+    DRB_CUDA(cudaMalloc((void**)&d_d, (size_t)n * 12));
+    DRB_CUDA(cudaMalloc((void**)&d_t, (size_t)n * 4));
+    DRB_CUDA(cudaMalloc((void**)&d_ids, (size_t)n * 4));
+    cudaMemcpyAsync(d_o, o3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_d, d3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
+    const uint32_t nn = (uint32_t)n;
+    k_load_rays<<<(nn + 255) / 256, 256, 0, stream>>>(d_o, d_d, nn, q);
+    k_prepare<<<1, 32, 0, stream>>>(q.counters, -1, 0, nn);
+    k_trace<<<rb->trace_blocks, 128, 0, stream>>>(dev_scene(s), scene_scale(s), q, 0);
+    k_store_ids<<<(nn + 255) / 256, 256, 0, stream>>>(q.hit, s->orig_id, nn, d_ids, d_t);
+    cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    if (t) cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_ids);
+    if (e != cudaSuccess) { drb_set_error("drb_trace_ids: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
+    return DRB_OK;
+}
+
+int drb_primary_rays(drb_scene* s, const drb_settings* settings, const drb_opts* opts, uint32_t sample, float* o3, float* d3)
+{
+    if (!s || !o3 || !d3) { drb_set_error("drb_primary_rays: null argument"); return DRB_ERR_ARG; }
+    if (int rc = check_settings(settings)) return rc;
+    DRB_CUDA(cudaSetDevice(s->device));
+    const int W = settings->width, H = settings->height;
+    FrameParams fp;
+    fp.W = W; fp.H = H; fp.tiles_x = (W + 7) / 8; fp.tiles_y = (H + 3) / 4;
+    fp.samples = 1; fp.sample_base = sample; fp.seed = opts ? opts->seed : 0;
+    fp.backtex = -1; fp.bg_intensity = 1; fp.scene_scale = scene_scale(s);
+    fp.cam = make_camera(*settings, W, H, 1);
+    const size_t nslots = (size_t)fp.tiles_x * fp.tiles_y * 32;
+    if (int rc = ensure_buffers(s, nslots)) return rc;
+    cudaStream_t stream = s->stream;
+    const size_t n = (size_t)W * H * 3;
+    float *d_o = nullptr, *d_d = nullptr;
+    DRB_CUDA(cudaMalloc((void**)&d_o, n * 4));
+    DRB_CUDA(cudaMalloc((void**)&d_d, n * 4));
+    k_generate<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q);
+    k_store_rays<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q, d_o, d_d);
+    cudaMemcpyAsync(o3, d_o, n * 4, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(d3, d_d, n * 4, cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_o); cudaFree(d_d);
+    if (e != cudaSuccess) { drb_set_error("drb_primary_rays: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
+    return DRB_OK;
+}
+
+int drb_tonemap_device(const float* accum_dev, int width, int height, double nsamples, uint8_t* rgb8_dev, void* stream)
+{
+    if (!accum_dev || !rgb8_dev || width <= 0 || height <= 0 || !(nsamples > 0)) { drb_set_error("drb_tonemap_device: bad argument"); return DRB_ERR_ARG; }
+    const size_t n = (size_t)width * height * 3;
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(accum_dev, n, (float)(1.0 / nsamples), rgb8_dev);
+    DRB_CUDA(cudaGetLastError());
+    return DRB_OK;
+}
+
+uint32_t drb_philox_word(uint64_t seed, uint32_t x, uint32_t y, uint32_t sample, uint32_t n)
+{
+    Philox4 p = philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), x, y, sample, n >> 2);
+    return p.v[n & 3u];
+}
+
+} // extern "C"

@@ -1,0 +1,416 @@
+// .rts scene ingest: replaces getnum / read / gettexnum / getppmnum / getppmpaths of the
+// reference (raygpu/kernel.cu:1113-1169, 1186-1530, 1172-1183, 1979-2018).
+//
+// Format: text, one record per line, comma separated.  First character
+// '/' = comment, '*' = settings line, anything else = object line of up to 38 columns.
+// The reference parses every number with std::stof / std::stoi (prefix parse, so
+// "45.000000" -> 45 for the integer fields); this loader produces bit-identical floats
+// (std::from_chars is correctly rounded, like strtof) but parses the file in one pass over
+// a memory map, in parallel over line ranges, instead of two stringstream passes.
+//
+// Deliberate differences from the reference, all on inputs it has undefined behaviour for:
+//   * blank lines are skipped (the reference throws from stof("")),
+//   * the token "r" ("random number", kernel.cu:1098-1102, 1308) becomes a deterministic hash
+//     of (line, column) in [0,1) instead of rand() seeded from the tick count,
+//   * fields a short line does not name are zero / the struct defaults (kernel.cu:48-74)
+//     instead of indeterminate heap contents,
+//   * there is no phantom object at index `lines` (kernel.cu:1158, 1518).
+#include "drb_internal.h"
+
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <mutex>
+#include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Token { const char* p; size_t n; };
+
+// std::stof semantics: skip leading white space, parse the longest valid prefix, fail if none.
+bool parse_float(Token t, float& out)
+{
+    const char* p = t.p; const char* e = t.p + t.n;
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\v' || *p == '\f')) ++p;
+    if (p < e && *p != '+') {
+        auto r = std::from_chars(p, e, out);
+        if (r.ec == std::errc()) return true;
+        if (r.ec == std::errc::result_out_of_range) {       // stof throws; saturate like strtof
+            out = (*p == '-') ? -HUGE_VALF : HUGE_VALF;
+            return true;
+        }
+    }
+    // rare spellings from_chars does not take ("+1", hex floats): strtof on a terminated copy
+    char buf[128];
+    size_t n = std::min((size_t)(e - p), sizeof buf - 1);
+    memcpy(buf, p, n); buf[n] = 0;
+    char* endp = nullptr;
+    float v = strtof(buf, &endp);
+    if (endp == buf) return false;
+    out = v;
+    return true;
+}
+
+// std::stoi semantics: base 10 prefix
+bool parse_int(Token t, int32_t& out)
+{
+    const char* p = t.p; const char* e = t.p + t.n;
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\v' || *p == '\f')) ++p;
+    bool neg = false;
+    if (p < e && (*p == '+' || *p == '-')) { neg = *p == '-'; ++p; }
+    if (p >= e || *p < '0' || *p > '9') return false;
+    long long v = 0;
+    while (p < e && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); if (v > 4294967296LL) v = 4294967296LL; ++p; }
+    if (neg) v = -v;
+    if (v > INT32_MAX) v = INT32_MAX;
+    if (v < INT32_MIN) v = INT32_MIN;
+    out = (int32_t)v;
+    return true;
+}
+
+inline bool token_is(Token t, const char* s) { size_t n = strlen(s); return t.n == n && memcmp(t.p, s, n) == 0; }
+
+float hash_unit(uint64_t line, uint32_t col)
+{
+    uint64_t z = line * 0x9E3779B97F4A7C15ull + col * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+void object_defaults(drb_object& o)
+{
+    memset(&o, 0, sizeof o);
+    // kernel.cu:55-64, 70-71
+    o.norm[0] = -2; o.norm[1] = -3; o.norm[2] = -20;
+    for (float* n : { o.n1, o.n2, o.n3 }) { n[0] = -2; n[1] = -3; n[2] = -20; }
+    o.t1[0] = 0; o.t1[1] = 1; o.t2[0] = 0; o.t2[1] = 0; o.t3[0] = 1; o.t3[1] = 0;
+    o.texnum = -1; o.rtexnum = -1;
+}
+
+struct ParseError { std::string msg; };
+
+// one object line -> drb_object; column map kernel.cu:1316-1503
+void parse_object_line(const char* p, const char* e, uint64_t lineno, const std::vector<std::string>& tex, drb_object& o)
+{
+    object_defaults(o);
+    int col = 0;
+    const char* q = p;
+    for (;;) {
+        const char* c = (const char*)memchr(q, ',', (size_t)(e - q));
+        Token t{ q, (size_t)((c ? c : e) - q) };
+        float f = 0; int32_t iv = 0;
+        bool is_r = token_is(t, "r");
+        auto F = [&]() -> float {
+            if (is_r) return hash_unit(lineno, (uint32_t)col);
+            if (!parse_float(t, f)) throw ParseError{ "line " + std::to_string(lineno) + " column " + std::to_string(col) + ": not a number: '" + std::string(t.p, t.n) + "'" };
+            return f;
+        };
+        auto I = [&]() -> int32_t {
+            if (is_r) return 0;                         // stoi("0.xxxxx") of the reference's random string
+            if (!parse_int(t, iv)) throw ParseError{ "line " + std::to_string(lineno) + " column " + std::to_string(col) + ": not an integer: '" + std::string(t.p, t.n) + "'" };
+            return iv;
+        };
+        switch (col) {
+        case 0: o.pos[0] = F(); break;   case 1: o.pos[1] = F(); break;   case 2: o.pos[2] = F(); break;
+        case 3: o.type = I(); break;
+        case 4: o.col[0] = F(); break;   case 5: o.col[1] = F(); break;   case 6: o.col[2] = F(); break;
+        case 7: o.add_y = F(); break;    case 8: o.add_x = F(); break;
+        case 9: o.dim[0] = F(); break;   case 10: o.dim[1] = F(); break;  case 11: o.dim[2] = F(); break;
+        case 12: o.mat = I(); break;
+        case 13: o.rot[0] = F(); break;  case 14: o.rot[1] = F(); break;  case 15: o.rot[2] = F(); break;
+        case 16: o.norm[0] = F(); break; case 17: o.norm[1] = F(); break; case 18: o.norm[2] = F(); break;
+        case 19: o.n1[0] = F(); break;   case 20: o.n1[1] = F(); break;   case 21: o.n1[2] = F(); break;
+        case 22: o.n2[0] = F(); break;   case 23: o.n2[1] = F(); break;   case 24: o.n2[2] = F(); break;
+        case 25: o.n3[0] = F(); break;   case 26: o.n3[1] = F(); break;   case 27: o.n3[2] = F(); break;
+        case 28: o.t1[0] = F(); break;   case 29: o.t1[1] = F(); break;
+        case 30: o.t2[0] = F(); break;   case 31: o.t2[1] = F(); break;
+        case 32: o.t3[0] = F(); break;   case 33: o.t3[1] = F(); break;
+        case 34: o.smooth = (I() == 1) ? 1 : 0; break;
+        case 35: o.checker = (I() == 1) ? 1 : 0; break;
+        case 36: if (!token_is(t, "no")) o.texnum = drb_find_texture(tex, std::string(t.p, t.n)); break;
+        case 37: if (!token_is(t, "no")) o.rtexnum = drb_find_texture(tex, std::string(t.p, t.n)); break;
+        default: break;                                 // the reference ignores further columns
+        }
+        ++col;
+        if (!c) break;
+        q = c + 1;
+    }
+    o.ncols = col;
+}
+
+// settings line, column map kernel.cu:1230-1293
+void parse_settings_line(const char* p, const char* e, uint64_t lineno, const std::vector<std::string>& tex, drb_settings& s)
+{
+    int col = 0;
+    const char* q = p;
+    for (;;) {
+        const char* c = (const char*)memchr(q, ',', (size_t)(e - q));
+        Token t{ q, (size_t)((c ? c : e) - q) };
+        float f = 0; int32_t iv = 0;
+        auto F = [&]() -> float {
+            if (!parse_float(t, f)) throw ParseError{ "settings line " + std::to_string(lineno) + " column " + std::to_string(col) + ": not a number: '" + std::string(t.p, t.n) + "'" };
+            return f;
+        };
+        auto I = [&]() -> int32_t {
+            if (!parse_int(t, iv)) throw ParseError{ "settings line " + std::to_string(lineno) + " column " + std::to_string(col) + ": not an integer: '" + std::string(t.p, t.n) + "'" };
+            return iv;
+        };
+        switch (col) {
+        case 1: s.cam[0] = F(); break;  case 2: s.cam[1] = F(); break;  case 3: s.cam[2] = F(); break;
+        case 4: s.aperture = F(); break;
+        case 5: s.look[0] = F(); break; case 6: s.look[1] = F(); break; case 7: s.look[2] = F(); break;
+        case 8: s.focus = F(); break;
+        case 9: s.fov = I(); break;
+        case 10: s.max_depth = I(); break;
+        case 11: s.spp = I(); break;
+        case 12: s.bg_intensity = F(); break;
+        case 13: if (!token_is(t, "no")) s.backtex = drb_find_texture(tex, std::string(t.p, t.n)); break;
+        case 14: s.width = I(); break;
+        case 15: s.height = I(); break;
+        default: break;
+        }
+        ++col;
+        if (!c) break;
+        q = c + 1;
+    }
+}
+
+int parse_buffer(const char* text, size_t len, const char* tex_dir, drb_host_scene** out)
+{
+    auto hs = new drb_host_scene();
+    drb_settings_default(&hs->settings);
+    hs->tex_paths = drb_scan_textures(tex_dir);
+
+    // pass 1: line table (std::getline semantics: a final line without '\n' counts, an empty tail does not)
+    struct Line { const char* b; const char* e; };
+    std::vector<Line> lines;
+    lines.reserve(len / 64 + 16);
+    const char* p = text; const char* end = text + len;
+    while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;
+        lines.push_back({ p, le });
+        p = nl ? nl + 1 : end;
+    }
+    // classify; object index = count of earlier object lines
+    std::vector<int64_t> obj_line;      // line number of each object
+    obj_line.reserve(lines.size());
+    std::string err;
+    for (size_t i = 0; i < lines.size(); ++i) {
+        const char* b = lines[i].b; const char* e = lines[i].e;
+        if (e > b && e[-1] == '\r') { --e; lines[i].e = e; }       // text-mode read on the reference's platform
+        if (b == e) {
+            hs->skipped++;
+            if (hs->first_warning.empty()) hs->first_warning = "line " + std::to_string(i + 1) + ": blank line skipped";
+            continue;
+        }
+        if (*b == '/') continue;
+        if (*b == '*') {
+            try { parse_settings_line(b, e, i + 1, hs->tex_paths, hs->settings); }
+            catch (ParseError& pe) { err = pe.msg; break; }
+            continue;
+        }
+        obj_line.push_back((int64_t)i);
+    }
+    if (!err.empty()) { drb_set_error("%s", err.c_str()); delete hs; return DRB_ERR_PARSE; }
+
+    // pass 2: objects, parallel over contiguous ranges
+    const int64_t n = (int64_t)obj_line.size();
+    hs->objects.resize((size_t)n);
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthreads = (int)std::min<int64_t>(hw ? hw : 4, std::max<int64_t>(1, n / 20000));
+    std::mutex err_mu;
+    int64_t err_line = INT64_MAX;
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            const Line& L = lines[(size_t)obj_line[k]];
+            try { parse_object_line(L.b, L.e, (uint64_t)obj_line[k] + 1, hs->tex_paths, hs->objects[(size_t)k]); }
+            catch (ParseError& pe) {
+                std::lock_guard<std::mutex> g(err_mu);
+                if (obj_line[k] < err_line) { err_line = obj_line[k]; err = pe.msg; }
+                return;
+            }
+        }
+    };
+    if (nthreads <= 1) work(0, n);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(work, n * t / nthreads, n * (t + 1) / nthreads);
+        for (auto& th : pool) th.join();
+    }
+    if (!err.empty()) { drb_set_error("%s", err.c_str()); delete hs; return DRB_ERR_PARSE; }
+
+    // objects the tracer cannot represent are kept (ids are line indices) but reported
+    for (int64_t k = 0; k < n; ++k) {
+        const drb_object& o = hs->objects[(size_t)k];
+        bool ok = (o.type == 2 && o.ncols >= 16) || (o.type == 0 && o.ncols >= 10);
+        if (!ok) {
+            hs->skipped++;
+            if (hs->first_warning.empty())
+                hs->first_warning = "line " + std::to_string(obj_line[k] + 1) + ": object with type " + std::to_string(o.type) + " and " +
+                                    std::to_string(o.ncols) + " columns is not renderable (types: 0 sphere, 2 triangle) and is left out of the tree";
+        }
+    }
+    if (!hs->first_warning.empty()) drb_set_error("%s", hs->first_warning.c_str());
+    *out = hs;
+    return DRB_OK;
+}
+
+} // namespace
+
+void drb_set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+void drb_clear_error() { g_last_error.clear(); }
+
+int drb_find_texture(const std::vector<std::string>& tex_paths, const std::string& query)
+{
+    for (size_t i = 0; i < tex_paths.size(); ++i) {
+        std::string low = tex_paths[i];
+        std::transform(low.begin(), low.end(), low.begin(), [](unsigned char c) { return (char)::tolower(c); });
+        if (low.find(query) != std::string::npos) return (int)i;
+    }
+    return -1;
+}
+
+std::vector<std::string> drb_scan_textures(const char* tex_dir)
+{
+    std::vector<std::string> found;
+    std::error_code ec;
+    std::filesystem::path dir = (tex_dir && tex_dir[0]) ? std::filesystem::path(tex_dir) : std::filesystem::current_path(ec);
+    if (ec) return found;
+    for (const auto& e : std::filesystem::directory_iterator(dir, ec)) {
+        std::string name = e.path().filename().string();
+        if (name.find("ppm") != std::string::npos || name.find("PPM") != std::string::npos) found.push_back(e.path().string());
+    }
+    std::sort(found.begin(), found.end());
+    return found;
+}
+
+extern "C" {
+
+const char* drb_last_error(void) { return g_last_error.c_str(); }
+int drb_abi_version(void) { return DRB_ABI_VERSION; }
+
+void drb_settings_default(drb_settings* s)
+{
+    if (!s) return;
+    memset(s, 0, sizeof *s);
+    s->cam[0] = 0; s->cam[1] = 0; s->cam[2] = 2;        // kernel.cu:125
+    s->aperture = 0.01f;                                // :127
+    s->focus = 3;                                       // :128
+    s->fov = 45; s->max_depth = 50; s->spp = 1;         // :130-132
+    s->bg_intensity = 1;                                // :108-109
+    s->backtex = -1;                                    // :123
+    s->width = 1280; s->height = 720;                   // :29-30
+}
+
+int drb_host_scene_parse(const char* text, size_t len, const char* tex_dir, drb_host_scene** out)
+{
+    if (!out || (!text && len)) { drb_set_error("drb_host_scene_parse: null argument"); return DRB_ERR_ARG; }
+    drb_clear_error();
+    *out = nullptr;
+    return parse_buffer(text ? text : "", len, tex_dir, out);
+}
+
+int drb_host_scene_load(const char* rts_path, const char* tex_dir, drb_host_scene** out)
+{
+    if (!rts_path || !out) { drb_set_error("drb_host_scene_load: null argument"); return DRB_ERR_ARG; }
+    drb_clear_error();
+    *out = nullptr;
+    int fd = open(rts_path, O_RDONLY);
+    if (fd < 0) { drb_set_error("cannot open scene file '%s': %s", rts_path, strerror(errno)); return DRB_ERR_IO; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); drb_set_error("'%s' is not a regular file", rts_path); return DRB_ERR_IO; }
+    size_t len = (size_t)st.st_size;
+    int rc;
+    if (len == 0) rc = parse_buffer("", 0, tex_dir, out);
+    else {
+        void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); drb_set_error("mmap of '%s' failed: %s", rts_path, strerror(errno)); return DRB_ERR_IO; }
+        madvise(m, len, MADV_SEQUENTIAL);
+        rc = parse_buffer((const char*)m, len, tex_dir, out);
+        munmap(m, len);
+    }
+    close(fd);
+    return rc;
+}
+
+int drb_host_scene_create(const drb_settings* settings, const drb_object* objects, int64_t nobjects,
+                          const char* const* tex_paths, int ntex, drb_host_scene** out)
+{
+    if (!out || nobjects < 0 || (nobjects && !objects) || ntex < 0 || (ntex && !tex_paths)) { drb_set_error("drb_host_scene_create: bad argument"); return DRB_ERR_ARG; }
+    drb_clear_error();
+    auto hs = new drb_host_scene();
+    if (settings) hs->settings = *settings; else drb_settings_default(&hs->settings);
+    hs->objects.assign(objects, objects + nobjects);
+    for (int i = 0; i < ntex; ++i) hs->tex_paths.emplace_back(tex_paths[i] ? tex_paths[i] : "");
+    *out = hs;
+    return DRB_OK;
+}
+
+void drb_host_scene_free(drb_host_scene* hs) { delete hs; }
+int64_t drb_host_scene_num_objects(const drb_host_scene* hs) { return hs ? (int64_t)hs->objects.size() : 0; }
+const drb_object* drb_host_scene_objects(const drb_host_scene* hs) { return hs && !hs->objects.empty() ? hs->objects.data() : nullptr; }
+int drb_host_scene_settings(const drb_host_scene* hs, drb_settings* out)
+{
+    if (!hs || !out) { drb_set_error("drb_host_scene_settings: null argument"); return DRB_ERR_ARG; }
+    *out = hs->settings;
+    return DRB_OK;
+}
+int drb_host_scene_num_textures(const drb_host_scene* hs) { return hs ? (int)hs->tex_paths.size() : 0; }
+const char* drb_host_scene_texture_path(const drb_host_scene* hs, int i)
+{
+    return (hs && i >= 0 && i < (int)hs->tex_paths.size()) ? hs->tex_paths[(size_t)i].c_str() : "";
+}
+int64_t drb_host_scene_num_skipped(const drb_host_scene* hs) { return hs ? hs->skipped : 0; }
+
+// writer in the exporter's format: plugin/rtsexport.py:205-207 (header + settings), :312-314 (objects)
+int drb_rts_write(const char* path, const drb_settings* s, const drb_object* objs, int64_t n,
+                  const char* const* tex_names, int ntex, const char* backtex_name)
+{
+    if (!path || !s || n < 0 || (n && !objs)) { drb_set_error("drb_rts_write: bad argument"); return DRB_ERR_ARG; }
+    FILE* f = fopen(path, "w");
+    if (!f) { drb_set_error("cannot create '%s': %s", path, strerror(errno)); return DRB_ERR_IO; }
+    std::vector<char> iobuf(1 << 22);
+    setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+    auto texname = [&](int k) -> const char* { return (k >= 0 && k < ntex && tex_names && tex_names[k]) ? tex_names[k] : "no"; };
+    fprintf(f, "/exported from dogeray_b200\n");
+    fprintf(f, "*,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%s,%i,%i\n", s->cam[0], s->cam[1], s->cam[2], s->aperture,
+            s->look[0], s->look[1], s->look[2], s->focus, (double)s->fov, (double)s->max_depth, (double)s->spp, s->bg_intensity,
+            backtex_name ? backtex_name : texname(s->backtex), s->width, s->height);
+    for (int64_t i = 0; i < n; ++i) {
+        const drb_object& o = objs[i];
+        fprintf(f, "%f,%f,%f,%d,%f,%f,%f,%f,%g,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%s,%s\n",
+                o.pos[0], o.pos[1], o.pos[2], o.type, o.col[0], o.col[1], o.col[2], o.add_y, o.add_x,
+                o.dim[0], o.dim[1], o.dim[2], (double)o.mat, o.rot[0], o.rot[1], o.rot[2],
+                o.norm[0], o.norm[1], o.norm[2], o.n1[0], o.n1[1], o.n1[2], o.n2[0], o.n2[1], o.n2[2], o.n3[0], o.n3[1], o.n3[2],
+                o.t1[0], o.t1[1], o.t2[0], o.t2[1], o.t3[0], o.t3[1], (double)o.smooth, (double)o.checker,
+                texname(o.texnum), texname(o.rtexnum));
+    }
+    bool ok = !ferror(f);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { drb_set_error("short write to '%s'", path); return DRB_ERR_IO; }
+    return DRB_OK;
+}
+
+} // extern "C"

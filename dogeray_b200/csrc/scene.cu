@@ -1,0 +1,550 @@
+// Device scene construction: upload + GPU LBVH build.  Replaces readtextures, build_bvh and the
+// per-frame scene upload inside CudaStarter (raygpu/kernel.cu:1915-1976, 1534-1909, 2604-2629).
+//
+// The reference builds a median-split tree on the host in ~4 s for 1 M triangles and re-uploads the
+// whole scene every frame.  Here the object lines are uploaded once and everything else happens on
+// the device:
+//   flag renderable objects -> exclusive scan (slot = rank among renderable objects, file order)
+//   pack Prim / ShadeRec / bounds per slot, reduce scene bounds (ordered-int atomics)
+//   63-bit Morton key of the box centre -> stable radix sort of (key, slot)
+//   Karras 2012 hierarchy over the sorted keys (ties broken by position)
+//   bottom-up refit with one atomic flag per internal node
+//   emit 64 B nodes that carry both child boxes
+// All floating-point steps that feed integer outputs (keys) use single IEEE operations (this TU is
+// compiled with -fmad=false), so oracle/lbvh_host.c reproduces keys, order and topology bit-exactly.
+#include "drb_internal.h"
+#include "device_scene.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+namespace {
+
+constexpr int kMaxTreeHeight = 96;      // traversal stack capacity in render.cu
+
+__host__ __device__ inline bool object_renderable(const drb_object& o)
+{
+    // same rule the loader reports with: SURVEY.md App. B.9 (types other than 0 / 2 are undefined
+    // behaviour in the reference) and junk lines that stop before the geometry columns
+    if (o.type == 2) return o.ncols == 0 || o.ncols >= 16;
+    if (o.type == 0) return o.ncols == 0 || o.ncols >= 10;
+    return false;
+}
+
+__device__ __forceinline__ int float_to_ordered(float f)
+{
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__host__ __device__ __forceinline__ float ordered_to_float(int i)
+{
+    int b = i >= 0 ? i : i ^ 0x7FFFFFFF;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+__global__ void k_flag(const drb_object* __restrict__ objs, int64_t n, int* __restrict__ flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = object_renderable(objs[i]) ? 1 : 0;
+}
+
+__global__ void k_init_bounds(int* b)
+{
+    if (threadIdx.x < 3) b[threadIdx.x] = 0x7FFFFFFF;            // min
+    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000;  // max
+}
+
+// one thread per object line
+__global__ void k_pack(const drb_object* __restrict__ objs, int64_t n, const int* __restrict__ flag, const int* __restrict__ slot,
+                       Prim* __restrict__ prims, ShadeRec* __restrict__ recs, int32_t* __restrict__ orig,
+                       float4* __restrict__ bmin, float4* __restrict__ bmax, int* __restrict__ scene_bounds)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+    bool live = i < n && flag[i];
+    if (live) {
+        const drb_object o = objs[i];
+        const int k = slot[i];
+        Prim p;
+        uint32_t flags = 0;
+        if (o.type == 0) {
+            const float r = fabsf(o.dim[0]);
+            p.a = make_float4(o.pos[0], o.pos[1], o.pos[2], __int_as_float(DRB_KIND_SPHERE));
+            p.b = make_float4(o.dim[0], 0.f, 0.f, 0.f);
+            p.c = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int a = 0; a < 3; ++a) { lo[a] = o.pos[a] - r; hi[a] = o.pos[a] + r; }
+            flags |= DRB_SF_SPHERE;
+        } else {
+            p.a = make_float4(o.pos[0], o.pos[1], o.pos[2], __int_as_float(DRB_KIND_TRI));
+            p.b = make_float4(o.dim[0] - o.pos[0], o.dim[1] - o.pos[1], o.dim[2] - o.pos[2], 0.f);
+            p.c = make_float4(o.rot[0] - o.pos[0], o.rot[1] - o.pos[1], o.rot[2] - o.pos[2], 0.f);
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = fminf(o.pos[a], fminf(o.dim[a], o.rot[a]));
+                hi[a] = fmaxf(o.pos[a], fmaxf(o.dim[a], o.rot[a]));
+            }
+            const bool face = o.norm[2] != -20.0f;
+            const bool smooth = face && o.n1[2] != -20.0f && o.smooth;
+            if (face) flags |= DRB_SF_FACE_NORMAL;
+            if (smooth) flags |= DRB_SF_SMOOTH;
+            if (o.checker) flags |= DRB_SF_CHECKER;
+            if (smooth || o.checker || o.texnum >= 0 || o.rtexnum >= 0) flags |= DRB_SF_NEEDS_UV;
+        }
+        prims[k] = p;
+        ShadeRec r;
+        r.r[0] = make_float4(o.norm[0], o.norm[1], o.norm[2], __uint_as_float(flags));
+        r.r[1] = make_float4(o.col[0], o.col[1], o.col[2], o.add_y);
+        r.r[2] = make_float4(o.add_x, __int_as_float(o.mat), __int_as_float(o.texnum), __int_as_float(o.rtexnum));
+        r.r[3] = make_float4(o.n1[0], o.n1[1], o.n1[2], o.t1[0]);
+        r.r[4] = make_float4(o.n2[0], o.n2[1], o.n2[2], o.t2[0]);
+        r.r[5] = make_float4(o.n3[0], o.n3[1], o.n3[2], o.t3[0]);
+        r.r[6] = make_float4(o.t1[1], o.t2[1], o.t3[1], 0.f);
+        r.r[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+        recs[k] = r;
+        orig[k] = (int32_t)i;
+        bmin[k] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        bmax[k] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    // warp-reduce the bounds, one atomic per warp and component
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float l = lo[a], h = hi[a];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, off));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, off));
+        }
+        if ((threadIdx.x & 31) == 0 && l <= h) {
+            atomicMin(&scene_bounds[a], float_to_ordered(l));
+            atomicMax(&scene_bounds[3 + a], float_to_ordered(h));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v)
+{
+    uint64_t x = v & 0x1FFFFFull;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+// 63-bit Morton key of the box centre, 21 bits per axis, x most significant
+__global__ void k_keys(const float4* __restrict__ bmin, const float4* __restrict__ bmax, int n, const int* __restrict__ scene_bounds,
+                       uint64_t* __restrict__ keys, int32_t* __restrict__ idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 lo = bmin[i], hi = bmax[i];
+    const float c[3] = { (lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f };
+    uint32_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float slo = ordered_to_float(scene_bounds[a]), shi = ordered_to_float(scene_bounds[3 + a]);
+        const float clo = slo, chi = shi;
+        float ext = chi - clo;
+        if (!(ext > 0.0f)) ext = 1.0f;
+        float x = ((c[a] - clo) / ext) * 2097152.0f;
+        x = fminf(fmaxf(x, 0.0f), 2097151.0f);
+        q[a] = (uint32_t)x;
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    idx[i] = i;
+}
+
+__global__ void k_gather(const int32_t* __restrict__ order, int n, const Prim* __restrict__ prims_u, const ShadeRec* __restrict__ recs_u,
+                         const int32_t* __restrict__ orig_u, const float4* __restrict__ bmin_u, const float4* __restrict__ bmax_u,
+                         Prim* __restrict__ prims, ShadeRec* __restrict__ recs, int32_t* __restrict__ orig,
+                         float4* __restrict__ lmin, float4* __restrict__ lmax)
+{
+    // 8 threads move one primitive: 3 + 8 float4 of payload
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = t >> 3, part = t & 7;
+    if (k >= n) return;
+    const int src = order[k];
+    const float4* rs = reinterpret_cast<const float4*>(recs_u + src);
+    float4* rd = reinterpret_cast<float4*>(recs + k);
+    rd[part] = rs[part];
+    if (part < 3) {
+        const float4* ps = reinterpret_cast<const float4*>(prims_u + src);
+        float4* pd = reinterpret_cast<float4*>(prims + k);
+        pd[part] = ps[part];
+    } else if (part == 3) {
+        orig[k] = orig_u[src];
+    } else if (part == 4) {
+        lmin[k] = bmin_u[src];
+    } else if (part == 5) {
+        lmax[k] = bmax_u[src];
+    }
+}
+
+// common-prefix length of sorted positions i and j; ties on the key fall back to the position
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a != b) return __clzll((long long)(a ^ b));
+    return 64 + __clz(i ^ j);
+}
+
+// Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees", HPG 2012, section 4
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int32_t* __restrict__ left, int32_t* __restrict__ right,
+                         int32_t* __restrict__ parent, int32_t* __restrict__ leaf_parent)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1; ; t = (t + 1) >> 1) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int lc = (lo == gamma) ? ~gamma : gamma;
+    const int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = lc; right[i] = rc;
+    if (lc < 0) leaf_parent[gamma] = i; else parent[gamma] = i;
+    if (rc < 0) leaf_parent[gamma + 1] = i; else parent[gamma + 1] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// one thread per leaf climbs; the second arrival at a node owns it
+__global__ void k_refit(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
+                        const int32_t* __restrict__ right, const int32_t* __restrict__ parent, const int32_t* __restrict__ leaf_parent,
+                        int* __restrict__ visits, float4* node_min, float4* node_max, int* __restrict__ height)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int node = leaf_parent[k];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&visits[node], 1) == 0) return;       // first arrival: sibling subtree not ready
+        __threadfence();
+        const int lc = left[node], rc = right[node];
+        const volatile float4* vmin = node_min; const volatile float4* vmax = node_max;
+        float4 a0, a1, b0, b1; int ha, hb;
+        if (lc < 0) { a0 = lmin[~lc]; a1 = lmax[~lc]; ha = 0; }
+        else { a0.x = vmin[lc].x; a0.y = vmin[lc].y; a0.z = vmin[lc].z; a0.w = vmin[lc].w; a1.x = vmax[lc].x; a1.y = vmax[lc].y; a1.z = vmax[lc].z; a1.w = 0; ha = __float_as_int(a0.w); }
+        if (rc < 0) { b0 = lmin[~rc]; b1 = lmax[~rc]; hb = 0; }
+        else { b0.x = vmin[rc].x; b0.y = vmin[rc].y; b0.z = vmin[rc].z; b0.w = vmin[rc].w; b1.x = vmax[rc].x; b1.y = vmax[rc].y; b1.z = vmax[rc].z; b1.w = 0; hb = __float_as_int(b0.w); }
+        const int h = max(ha, hb) + 1;
+        node_min[node] = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), __int_as_float(h));   // .w carries the subtree height
+        node_max[node] = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.f);
+        if (node == 0) *height = h;
+        node = parent[node];
+    }
+}
+
+__global__ void k_emit_nodes(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
+                             const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
+                             BvhNode* __restrict__ nodes)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int lc = left[i], rc = right[i];
+    const float4 a0 = lc < 0 ? lmin[~lc] : node_min[lc], a1 = lc < 0 ? lmax[~lc] : node_max[lc];
+    const float4 b0 = rc < 0 ? lmin[~rc] : node_min[rc], b1 = rc < 0 ? lmax[~rc] : node_max[rc];
+    BvhNode nd;
+    nd.c0xy = make_float4(a0.x, a1.x, a0.y, a1.y);
+    nd.c1xy = make_float4(b0.x, b1.x, b0.y, b1.y);
+    nd.cz = make_float4(a0.z, a1.z, b0.z, b1.z);
+    nd.link = make_int4(lc, rc, 0, 0);
+    nodes[i] = nd;
+}
+
+// a tree of one primitive: child0 = the leaf, child1 = an empty box
+__global__ void k_emit_single(const float4* __restrict__ lmin, const float4* __restrict__ lmax, BvhNode* __restrict__ nodes)
+{
+    const float4 a0 = lmin[0], a1 = lmax[0];
+    BvhNode nd;
+    nd.c0xy = make_float4(a0.x, a1.x, a0.y, a1.y);
+    nd.c1xy = make_float4(3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f);
+    nd.cz = make_float4(a0.z, a1.z, 3.0e38f, -3.0e38f);
+    nd.link = make_int4(~0, ~0, 0, 0);
+    nodes[0] = nd;
+}
+
+template <typename T> int dev_alloc(T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    DRB_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    return DRB_OK;
+}
+
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T> int alloc(T** p, size_t count)
+    {
+        int rc = dev_alloc(p, count);
+        if (rc == DRB_OK) ptrs.push_back(*p);
+        return rc;
+    }
+};
+
+int build_tree(drb_scene* s, const drb_host_scene* hs)
+{
+    const int64_t nobj = (int64_t)hs->objects.size();
+    if (nobj >= (1ll << 31) - 8) { drb_set_error("too many objects (%lld)", (long long)nobj); return DRB_ERR_UNSUPPORTED; }
+    cudaStream_t st = s->stream;
+    Scratch tmp;
+    cudaEvent_t e0, e1, e2;
+    DRB_CUDA(cudaEventCreate(&e0)); DRB_CUDA(cudaEventCreate(&e1)); DRB_CUDA(cudaEventCreate(&e2));
+    DRB_CUDA(cudaEventRecord(e0, st));
+
+    drb_object* d_objs = nullptr; int* d_flag = nullptr; int* d_slot = nullptr; int* d_bounds = nullptr;
+    if (int rc = tmp.alloc(&d_objs, (size_t)nobj)) return rc;
+    if (int rc = tmp.alloc(&d_flag, (size_t)nobj + 1)) return rc;
+    if (int rc = tmp.alloc(&d_slot, (size_t)nobj + 1)) return rc;
+    if (int rc = tmp.alloc(&d_bounds, 8)) return rc;
+    if (nobj) DRB_CUDA(cudaMemcpyAsync(d_objs, hs->objects.data(), (size_t)nobj * sizeof(drb_object), cudaMemcpyHostToDevice, st));
+    DRB_CUDA(cudaEventRecord(e1, st));
+
+    const int T = 256;
+    int nprims = 0;
+    if (nobj) {
+        k_flag<<<(unsigned)((nobj + T - 1) / T), T, 0, st>>>(d_objs, nobj, d_flag);
+        size_t scan_bytes = 0;
+        DRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag, d_slot, (int)nobj, st));
+        void* d_scan = nullptr;
+        if (int rc = tmp.alloc((char**)&d_scan, scan_bytes)) return rc;
+        DRB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_flag, d_slot, (int)nobj, st));
+        int last_slot = 0, last_flag = 0;
+        DRB_CUDA(cudaMemcpyAsync(&last_slot, d_slot + nobj - 1, 4, cudaMemcpyDeviceToHost, st));
+        DRB_CUDA(cudaMemcpyAsync(&last_flag, d_flag + nobj - 1, 4, cudaMemcpyDeviceToHost, st));
+        DRB_CUDA(cudaStreamSynchronize(st));
+        nprims = last_slot + last_flag;
+    }
+    s->nobjects = nobj;
+    s->nprims = nprims;
+    s->nnodes = nprims == 0 ? 0 : std::max(1, nprims - 1);
+    memset(&s->info, 0, sizeof s->info);
+    s->info.nprims = nprims; s->info.nnodes = s->nnodes;
+
+    if (int rc = dev_alloc(&s->prims, (size_t)nprims)) return rc;
+    if (int rc = dev_alloc(&s->recs, (size_t)nprims)) return rc;
+    if (int rc = dev_alloc(&s->orig_id, (size_t)nprims)) return rc;
+    if (int rc = dev_alloc(&s->nodes, (size_t)s->nnodes)) return rc;
+    const size_t nint = nprims > 1 ? (size_t)nprims - 1 : 1;
+    if (int rc = dev_alloc(&s->dbg.keys, (size_t)nprims)) return rc;
+    if (int rc = dev_alloc(&s->dbg.order, (size_t)nprims)) return rc;
+    if (int rc = dev_alloc(&s->dbg.parent, nint)) return rc;
+    if (int rc = dev_alloc(&s->dbg.left, nint)) return rc;
+    if (int rc = dev_alloc(&s->dbg.right, nint)) return rc;
+    if (int rc = dev_alloc(&s->dbg.node_min, nint)) return rc;
+    if (int rc = dev_alloc(&s->dbg.node_max, nint)) return rc;
+
+    int height = 0;
+    if (nprims > 0) {
+        Prim* prims_u; ShadeRec* recs_u; int32_t* orig_u; float4 *bmin_u, *bmax_u, *lmin, *lmax;
+        uint64_t* keys_u; int32_t* idx_u; int32_t* leaf_parent; int* visits; int* d_height;
+        if (int rc = tmp.alloc(&prims_u, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&recs_u, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&orig_u, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&bmin_u, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&bmax_u, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&lmin, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&lmax, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&keys_u, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&idx_u, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&leaf_parent, (size_t)nprims)) return rc;
+        if (int rc = tmp.alloc(&visits, nint)) return rc;
+        if (int rc = tmp.alloc(&d_height, 1)) return rc;
+
+        k_init_bounds<<<1, 32, 0, st>>>(d_bounds);
+        k_pack<<<(unsigned)((nobj + T - 1) / T), T, 0, st>>>(d_objs, nobj, d_flag, d_slot, prims_u, recs_u, orig_u, bmin_u, bmax_u, d_bounds);
+        k_keys<<<(nprims + T - 1) / T, T, 0, st>>>(bmin_u, bmax_u, nprims, d_bounds, keys_u, idx_u);
+        size_t sort_bytes = 0;
+        DRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_u, s->dbg.keys, idx_u, s->dbg.order, nprims, 0, 63, st));
+        void* d_sort = nullptr;
+        if (int rc = tmp.alloc((char**)&d_sort, sort_bytes)) return rc;
+        DRB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_u, s->dbg.keys, idx_u, s->dbg.order, nprims, 0, 63, st));
+        {
+            const long long threads = (long long)nprims * 8;
+            k_gather<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(s->dbg.order, nprims, prims_u, recs_u, orig_u, bmin_u, bmax_u,
+                                                                      s->prims, s->recs, s->orig_id, lmin, lmax);
+        }
+        if (nprims > 1) {
+            DRB_CUDA(cudaMemsetAsync(visits, 0, nint * sizeof(int), st));
+            DRB_CUDA(cudaMemsetAsync(d_height, 0, sizeof(int), st));
+            k_karras<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(s->dbg.keys, nprims, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent);
+            k_refit<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent, visits,
+                                                       s->dbg.node_min, s->dbg.node_max, d_height);
+            k_emit_nodes<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.node_min, s->dbg.node_max, s->nodes);
+            DRB_CUDA(cudaMemcpyAsync(&height, d_height, 4, cudaMemcpyDeviceToHost, st));
+        } else {
+            k_emit_single<<<1, 1, 0, st>>>(lmin, lmax, s->nodes);
+            height = 1;
+        }
+        int hb[6];
+        DRB_CUDA(cudaMemcpyAsync(hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
+        DRB_CUDA(cudaEventRecord(e2, st));
+        DRB_CUDA(cudaStreamSynchronize(st));
+        DRB_CUDA(cudaGetLastError());
+        for (int a = 0; a < 3; ++a) { s->info.bounds_min[a] = ordered_to_float(hb[a]); s->info.bounds_max[a] = ordered_to_float(hb[3 + a]); }
+    } else {
+        DRB_CUDA(cudaEventRecord(e2, st));
+        DRB_CUDA(cudaStreamSynchronize(st));
+    }
+    s->info.max_depth = height;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1); s->info.upload_ms = ms;
+    cudaEventElapsedTime(&ms, e1, e2); s->info.build_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (height > kMaxTreeHeight) {
+        drb_set_error("LBVH height %d exceeds the traversal stack (%d)", height, kMaxTreeHeight);
+        return DRB_ERR_UNSUPPORTED;
+    }
+    return DRB_OK;
+}
+
+int upload_textures(drb_scene* s, const drb_host_scene* hs)
+{
+    const int nt = (int)hs->tex_paths.size();
+    s->ntextures = nt;
+    std::vector<char> used((size_t)std::max(nt, 1), 0);
+    auto mark = [&](int k) { if (k >= 0 && k < nt) used[(size_t)k] = 1; };
+    mark(hs->settings.backtex);
+    for (const drb_object& o : hs->objects) { mark(o.texnum); mark(o.rtexnum); }
+    std::vector<DevTexture> table((size_t)std::max(nt, 1));
+    for (int i = 0; i < nt; ++i) {
+        table[(size_t)i] = DevTexture{ nullptr, 0, 0 };
+        drb_image img;
+        int rc = drb_load_ppm(hs->tex_paths[(size_t)i], img);
+        if (rc != DRB_OK) {
+            if (used[(size_t)i]) return rc;             // a texture the scene names must load
+            continue;                                   // the reference loads every .ppm it finds; unused ones may be anything
+        }
+        void* d = nullptr;
+        DRB_CUDA(cudaMalloc(&d, img.rgba.size()));
+        s->texture_storage.push_back(d);
+        DRB_CUDA(cudaMemcpy(d, img.rgba.data(), img.rgba.size(), cudaMemcpyHostToDevice));
+        table[(size_t)i] = DevTexture{ (const uchar4*)d, img.w, img.h };
+    }
+    if (int rc = dev_alloc(&s->textures, table.size())) return rc;
+    DRB_CUDA(cudaMemcpy(s->textures, table.data(), table.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
+    drb_clear_error();
+    return DRB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int drb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void drb_scene_free(drb_scene* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    drb_render_buffers_free(s);
+    cudaFree(s->nodes); cudaFree(s->prims); cudaFree(s->recs); cudaFree(s->orig_id); cudaFree(s->textures);
+    for (void* p : s->texture_storage) cudaFree(p);
+    cudaFree(s->dbg.keys); cudaFree(s->dbg.order); cudaFree(s->dbg.parent); cudaFree(s->dbg.left); cudaFree(s->dbg.right);
+    cudaFree(s->dbg.node_min); cudaFree(s->dbg.node_max);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out)
+{
+    if (!hs || !out) { drb_set_error("drb_scene_create: null argument"); return DRB_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        drb_set_error("no CUDA device available (dogeray_b200 has no CPU path)");
+        return DRB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { drb_set_error("device %d out of range (0..%d)", device, ndev - 1); return DRB_ERR_ARG; }
+    DRB_CUDA(cudaSetDevice(device));
+    auto s = new drb_scene();
+    s->device = device;
+    s->settings = hs->settings;
+    cudaError_t ce = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { drb_set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); delete s; return DRB_ERR_CUDA; }
+    int rc = upload_textures(s, hs);
+    if (rc == DRB_OK) rc = build_tree(s, hs);
+    if (rc != DRB_OK) { std::string keep = drb_last_error(); drb_scene_free(s); drb_set_error("%s", keep.c_str()); return rc; }
+    if (s->settings.backtex >= s->ntextures) s->settings.backtex = -1;
+    *out = s;
+    return DRB_OK;
+}
+
+int drb_scene_load(const char* rts_path, const char* tex_dir, int device, drb_scene** out)
+{
+    if (!out) { drb_set_error("drb_scene_load: null argument"); return DRB_ERR_ARG; }
+    drb_host_scene* hs = nullptr;
+    int rc = drb_host_scene_load(rts_path, tex_dir, &hs);
+    if (rc != DRB_OK) return rc;
+    rc = drb_scene_create(hs, device, out);
+    drb_host_scene_free(hs);
+    return rc;
+}
+
+int drb_scene_settings(const drb_scene* s, drb_settings* out)
+{
+    if (!s || !out) { drb_set_error("drb_scene_settings: null argument"); return DRB_ERR_ARG; }
+    *out = s->settings;
+    return DRB_OK;
+}
+int64_t drb_scene_num_prims(const drb_scene* s) { return s ? s->nprims : 0; }
+int64_t drb_scene_num_objects(const drb_scene* s) { return s ? s->nobjects : 0; }
+int drb_scene_build_info(const drb_scene* s, drb_build_info* out)
+{
+    if (!s || !out) { drb_set_error("drb_scene_build_info: null argument"); return DRB_ERR_ARG; }
+    *out = s->info;
+    return DRB_OK;
+}
+
+int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* parent, int32_t* left, int32_t* right,
+                   float* node_min, float* node_max)
+{
+    if (!s) { drb_set_error("drb_scene_lbvh: null scene"); return DRB_ERR_ARG; }
+    DRB_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->nprims, ni = n > 1 ? n - 1 : 0;
+    if (keys && n) DRB_CUDA(cudaMemcpy(keys, s->dbg.keys, n * 8, cudaMemcpyDeviceToHost));
+    if (order && n) DRB_CUDA(cudaMemcpy(order, s->dbg.order, n * 4, cudaMemcpyDeviceToHost));
+    if (parent && ni) DRB_CUDA(cudaMemcpy(parent, s->dbg.parent, ni * 4, cudaMemcpyDeviceToHost));
+    if (left && ni) DRB_CUDA(cudaMemcpy(left, s->dbg.left, ni * 4, cudaMemcpyDeviceToHost));
+    if (right && ni) DRB_CUDA(cudaMemcpy(right, s->dbg.right, ni * 4, cudaMemcpyDeviceToHost));
+    if ((node_min || node_max) && ni) {
+        std::vector<float4> tmp(ni);
+        if (node_min) {
+            DRB_CUDA(cudaMemcpy(tmp.data(), s->dbg.node_min, ni * 16, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < ni; ++i) { node_min[3*i] = tmp[i].x; node_min[3*i+1] = tmp[i].y; node_min[3*i+2] = tmp[i].z; }
+        }
+        if (node_max) {
+            DRB_CUDA(cudaMemcpy(tmp.data(), s->dbg.node_max, ni * 16, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < ni; ++i) { node_max[3*i] = tmp[i].x; node_max[3*i+1] = tmp[i].y; node_max[3*i+2] = tmp[i].z; }
+        }
+    }
+    return DRB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,206 @@
+/* dogeray_b200 -- C ABI of the B200-native path tracer that replaces the hot path of
+ * PhilipPragerUrbina/DOGERAY's raygpu/kernel.cu (".rts in -> path-traced image out").
+ *
+ * The reference has no plugin/FFI interface; its de-facto boundary is
+ *     cudaError_t CudaStarter(int3* outputr, bvh* nbvhtree, singleobject* allobjects,
+ *                             cudaTextureObject_t* texarray, int divisor)
+ * (raygpu/kernel.cu:138, :2562-2669) plus the file-scope settings it reads
+ * (kernel.cu:29-30, 119-132) and the start-up sequence of main() (kernel.cu:2055-2103:
+ * getnum -> read -> readtextures -> build_bvh).  Each entry point below says which of
+ * those it replaces.
+ *
+ * Conventions: plain C types only; every function returns DRB_OK (0) or a negative
+ * drb_status and never throws; drb_last_error() holds the message of the last failure
+ * on the calling thread.  A drb_scene lives on ONE CUDA device and is not thread-safe
+ * (one call at a time per handle).  There is no CPU fallback: without a usable CUDA
+ * device every device entry point fails with DRB_ERR_CUDA.
+ */
+#ifndef DOGERAY_B200_H
+#define DOGERAY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRB_ABI_VERSION 1
+
+typedef enum drb_status {
+    DRB_OK = 0,
+    DRB_ERR_ARG = -1,       /* bad argument */
+    DRB_ERR_IO = -2,        /* file cannot be opened / short read / short write */
+    DRB_ERR_PARSE = -3,     /* malformed .rts or .ppm content */
+    DRB_ERR_CUDA = -4,      /* CUDA runtime error, or no device */
+    DRB_ERR_NOMEM = -5,
+    DRB_ERR_UNSUPPORTED = -6
+} drb_status;
+
+/* ---- the settings line of a .rts file ------------------------------------------------
+ * "*,camx,camy,camz,aperture,lookx,looky,lookz,focus,fov,maxdepth,spp,bgintensity,backtex,W,H"
+ * (writer plugin/rtsexport.py:207, reader kernel.cu:1223-1299).  Defaults are the
+ * file-scope initialisers kernel.cu:29-30, 119-132.  These are also the 13 floats
+ * CudaStarter packs into settings[] (kernel.cu:2581). */
+typedef struct drb_settings {
+    float cam[3];           /* campos            default 0,0,2 */
+    float aperture;         /* aperturee         default 0.01  */
+    float look[3];          /* look              default 0,0,0 */
+    float focus;            /* focus_diste       default 3     */
+    int32_t fov;            /* fovv, degrees, vertical; default 45 */
+    int32_t max_depth;      /* max_depthh        default 50    */
+    int32_t spp;            /* samples_per_pixell default 1    */
+    float bg_intensity;     /* backgroundintensity default 1   */
+    int32_t backtex;        /* index into the scene's texture table, -1 = sky gradient */
+    int32_t width;          /* SCREEN_WIDTH      default 1280  */
+    int32_t height;         /* SCREEN_HEIGHT     default 720   */
+} drb_settings;
+
+/* ---- one object line of a .rts file ---------------------------------------------------
+ * Column meaning: SURVEY.md App. A.2; reader kernel.cu:1316-1503; the in-memory layout the
+ * reference parses into is `singleobject` (kernel.cu:48-74).  This struct is the
+ * file-format view (what a loader or a scene writer exchanges), not the device layout. */
+typedef struct drb_object {
+    float pos[3];           /* col 0-2   triangle v0 / sphere centre */
+    int32_t type;           /* col 3     0 sphere, 2 triangle */
+    float col[3];           /* col 4-6 */
+    float add_y;            /* col 7     roughness, or IOR for glass (addional.y) */
+    float add_x;            /* col 8     != 0 -> normalised diffuse lobe (addional.x) */
+    float dim[3];           /* col 9-11  triangle v1 / sphere radius in [0] */
+    int32_t mat;            /* col 12    0 diffuse, 2 mirror, 3 metal, 4 glass, 5 glossy, other emissive */
+    float rot[3];           /* col 13-15 triangle v2 */
+    float norm[3];          /* col 16-18 face normal, sentinel z == -20 */
+    float n1[3], n2[3], n3[3]; /* col 19-27 vertex normals, sentinel z == -20 */
+    float t1[2], t2[2], t3[2]; /* col 28-33 UVs, defaults (0,1) (0,0) (1,0) */
+    int32_t smooth;         /* col 34 */
+    int32_t checker;        /* col 35    `tex` flag: procedural checker */
+    int32_t texnum;         /* col 36    colour texture index or -1 */
+    int32_t rtexnum;        /* col 37    roughness texture index or -1 */
+    int32_t ncols;          /* how many columns the line had (0 for objects made in memory) */
+} drb_object;
+
+/* ---- host-side scene description: replaces getnum + read + getppmpaths (kernel.cu:1113-1530,
+ * 1979-2018).  Pure host code, no CUDA. ------------------------------------------------- */
+typedef struct drb_host_scene drb_host_scene;
+
+/* Parse `rts_path`.  Textures are looked up by name among the files of `tex_dir` whose name
+ * contains "ppm"/"PPM" (NULL -> current working directory, as the reference does), visited in
+ * sorted order; the lower-cased path must contain the (unmodified) query, kernel.cu:1172-1183. */
+int drb_host_scene_load(const char* rts_path, const char* tex_dir, drb_host_scene** out);
+/* Same from a memory buffer holding .rts text. */
+int drb_host_scene_parse(const char* text, size_t len, const char* tex_dir, drb_host_scene** out);
+/* Build one from arrays (synthetic scenes).  `tex_paths` may be NULL when ntex == 0. */
+int drb_host_scene_create(const drb_settings* settings, const drb_object* objects, int64_t nobjects,
+                          const char* const* tex_paths, int ntex, drb_host_scene** out);
+void drb_host_scene_free(drb_host_scene* hs);
+int64_t drb_host_scene_num_objects(const drb_host_scene* hs);
+const drb_object* drb_host_scene_objects(const drb_host_scene* hs);
+int drb_host_scene_settings(const drb_host_scene* hs, drb_settings* out);
+int drb_host_scene_num_textures(const drb_host_scene* hs);
+const char* drb_host_scene_texture_path(const drb_host_scene* hs, int i);
+/* lines skipped while parsing (unsupported type, junk line); see drb_last_error() for the first */
+int64_t drb_host_scene_num_skipped(const drb_host_scene* hs);
+/* Write a scene in the exporter's format (plugin/rtsexport.py:207, 312-314). */
+int drb_rts_write(const char* path, const drb_settings* settings, const drb_object* objects, int64_t nobjects,
+                  const char* const* tex_names, int ntex, const char* backtex_name);
+void drb_settings_default(drb_settings* out);
+
+/* ---- device scene: replaces readtextures + build_bvh + the per-frame upload inside
+ * CudaStarter (kernel.cu:1915-1976, 1864-1909, 2604-2629).  Uploads once, builds the LBVH on the
+ * GPU, keeps everything resident. ----------------------------------------------------- */
+typedef struct drb_scene drb_scene;
+
+int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out);
+/* convenience: drb_host_scene_load + drb_scene_create */
+int drb_scene_load(const char* rts_path, const char* tex_dir, int device, drb_scene** out);
+void drb_scene_free(drb_scene* s);
+int drb_scene_settings(const drb_scene* s, drb_settings* out);
+int64_t drb_scene_num_prims(const drb_scene* s);       /* primitives in the tree */
+int64_t drb_scene_num_objects(const drb_scene* s);     /* object lines (ids index these) */
+
+typedef struct drb_build_info {
+    int64_t nprims, nnodes;
+    float bounds_min[3], bounds_max[3];
+    float upload_ms, build_ms;
+    int32_t max_depth;
+} drb_build_info;
+int drb_scene_build_info(const drb_scene* s, drb_build_info* out);
+
+/* Integer outputs of the GPU LBVH build, for the bit-exact check against a host build.
+ * Any pointer may be NULL.  keys: n 64-bit sort keys in sorted order; order: n prim slots in
+ * sorted order; parent/left/right: n-1 internal nodes, children >= 0 are internal nodes,
+ * children < 0 are leaves encoded as ~sorted_position; node_min/node_max: 3 floats per
+ * internal node. */
+int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* parent, int32_t* left, int32_t* right,
+                   float* node_min, float* node_max);
+
+/* ---- rendering ------------------------------------------------------------------------ */
+typedef struct drb_opts {
+    uint64_t seed;              /* Philox key */
+    uint32_t sample_base;       /* first sample index of this call */
+    uint32_t sample_count;      /* samples per pixel to trace in this call; 0 -> settings->spp */
+    uint32_t batch_paths;       /* paths in flight per wavefront batch; 0 -> default */
+    uint32_t flags;             /* DRB_FLAG_* */
+    void* stream;               /* cudaStream_t to launch on; NULL -> the scene's own stream */
+} drb_opts;
+#define DRB_FLAG_ACCUMULATE 1u  /* add into accum instead of overwriting it */
+
+typedef struct drb_stats {
+    uint64_t paths;             /* camera paths traced */
+    uint64_t rays;              /* closest-hit queries (one per hit() call of the reference, kernel.cu:800) */
+    float trace_ms;             /* device time of the closest-hit kernel, summed over launches */
+    float total_ms;             /* device time of the whole call */
+    uint32_t trace_launches;
+    uint32_t kernel_launches;
+} drb_stats;
+
+void drb_opts_default(drb_opts* out);
+
+/* Replaces the accumulate loop of main() (kernel.cu:2154-2224) and every CudaStarter call in
+ * it: traces `sample_count` samples for every pixel and writes the SUM of radiance, row-major,
+ * 3 floats per pixel, index (y*W + x)*3, linear, unclamped.  Divide by the sample count for the
+ * mean.  accum_dev is a DEVICE pointer (W*H*3 floats); the call is asynchronous on opts->stream
+ * unless `stats` is non-NULL, in which case it synchronises to fill it. */
+int drb_render_device(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_dev, drb_stats* stats);
+/* Same with a HOST accumulation buffer (synchronous; includes the device->host copy). */
+int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats);
+
+/* Exact output contract of CudaStarter (kernel.cu:2562-2669, Kernel :998-1093): out[(x*H + y)*3 + c] =
+ * trunc(255 * mean radiance) for x < W/divisor/8*8, y < H/divisor/8*8, other entries untouched.
+ * `out` is a host buffer of W*H*3 int32. */
+int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opts, int divisor, int32_t* out);
+
+/* Closest-hit object ids (index of the object line, -1 = miss) and distances for explicit rays:
+ * the same query as hit() (kernel.cu:468-512).  o3/d3: n*3 floats on the host. */
+int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int32_t* ids, float* t);
+/* The camera rays of sample `sample` for every pixel, row-major (y*W + x): what Kernel computes at
+ * kernel.cu:1067-1076.  o3/d3: W*H*3 floats on the host. */
+int drb_primary_rays(drb_scene* s, const drb_settings* settings, const drb_opts* opts, uint32_t sample, float* o3, float* d3);
+
+/* The display transform of main() (kernel.cu:2287): 8-bit = clamp(trunc(255 * sum / nsamples), 0, 255),
+ * linear, no gamma.  accum row-major W*H*3 floats (host); rgb8 W*H*3 bytes, row-major, y = 0 at the top. */
+int drb_tonemap(const float* accum_host, int width, int height, double nsamples, uint8_t* rgb8);
+/* Device variant, asynchronous on `stream`: used after an NCCL reduce on rank 0. */
+int drb_tonemap_device(const float* accum_dev, int width, int height, double nsamples, uint8_t* rgb8_dev, void* stream);
+
+/* ---- image files ---------------------------------------------------------------------- */
+/* 32-bpp BITMAPV4HEADER BMP exactly as SDL_SaveBMP writes the reference's screenshots
+ * (kernel.cu:2505-2513; layout pinned by images/ *.bmp). */
+int drb_write_bmp(const char* path, const uint8_t* rgb8, int width, int height);
+int drb_write_ppm(const char* path, const uint8_t* rgb8, int width, int height);
+/* P6/P5 -> RGBA8 with alpha 0, rows top-down (what sdkLoadPPM4 hands readtextures, kernel.cu:1926).
+ * *rgba is malloc'd; release with drb_free. */
+int drb_read_ppm(const char* path, uint8_t** rgba, int* width, int* height);
+void drb_free(void* p);
+
+/* ---- misc ------------------------------------------------------------------------------ */
+const char* drb_last_error(void);
+int drb_abi_version(void);
+int drb_device_count(void);
+/* word `n` of the sampler stream of pixel (x, y), sample `sample` (Philox4x32-10) */
+uint32_t drb_philox_word(uint64_t seed, uint32_t x, uint32_t y, uint32_t sample, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOGERAY_B200_H */
