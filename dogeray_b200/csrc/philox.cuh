@@ -2,11 +2,11 @@
 // raygpu/kernel.cu:1061-1065 and every curand_uniform_double call, kernel.cu:644, 657, 1067-1068).
 //
 //   word(seed, x, y, sample, n) = Philox4x32-10(key = {seed.lo, seed.hi}, ctr = {x, y, sample, n >> 2})[n & 3]
-//   uniform(n)                  = ((word >> 8) + 0.5) * 2^-24        in (0,1), on a 24-bit grid
+//   uniform(n)                  = float((word >> 8) + 0.5f) * 2^-24   in (0,1] (k + 0.5 rounds in float for k >= 2^23)
 //
 // n is the running draw index of one (pixel, sample) path, consumed in the reference's call order
 // (jitter u, jitter v, lens disk attempts, then per bounce what the material draws).  Because every
-// uniform is a float-exact multiple of 2^-25, the reference's `u * 2 - 1` evaluated in double and
+// uniform is a float on the 2^-25 grid, the reference's `u * 2 - 1` evaluated in double and
 // rounded to float equals the same expression evaluated in float.
 #pragma once
 #include <cstdint>

@@ -1,0 +1,135 @@
+/* TEST INFRASTRUCTURE -- host build of the LBVH, the bit-exact check target for the GPU builder
+ * (dogeray_b200/csrc/scene.cu).  The reference has no LBVH (its build_bvh, kernel.cu:1864-1909, is a
+ * host median split, restated in dogeray_oracle.c); this file restates the PRODUCT's build steps in
+ * scalar C so that its integer outputs -- Morton keys, sorted order, Karras topology -- and the
+ * refitted boxes can be compared with what the device produced, bit for bit.
+ *
+ * Steps (same single IEEE operations as the device code; compile with -ffp-contract=off):
+ *   scene bounds = min / max over primitive boxes
+ *   key = 63-bit Morton code of the box centre ((lo + hi) * 0.5), 21 bits per axis, x most significant,
+ *         axis value = (uint)clamp(((c - slo) / ext) * 2097152, 0, 2097151), ext = shi - slo or 1 if not > 0
+ *   stable sort of (key, slot)
+ *   Karras 2012 hierarchy, delta(i, j) = clz64(key_i ^ key_j), or 64 + clz32(i ^ j) when the keys tie
+ *   bottom-up box union
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+static uint64_t spread21(uint32_t v)
+{
+    uint64_t x = v & 0x1FFFFFull;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+typedef struct { uint64_t key; int32_t slot; } kv;
+static int kv_cmp(const void* a, const void* b)
+{
+    const kv* p = (const kv*)a; const kv* q = (const kv*)b;
+    if (p->key != q->key) return p->key < q->key ? -1 : 1;
+    return (p->slot > q->slot) - (p->slot < q->slot);          /* = stable order of the radix sort */
+}
+
+static int delta(const uint64_t* keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a != b) return __builtin_clzll(a ^ b);
+    return 64 + __builtin_clz((unsigned)(i ^ j));
+}
+
+static void node_box(int c, const float* lmin, const float* lmax, const float* nmin, const float* nmax, float lo[3], float hi[3])
+{
+    const float* a = c < 0 ? lmin + 3 * (size_t)(~c) : nmin + 3 * (size_t)c;
+    const float* b = c < 0 ? lmax + 3 * (size_t)(~c) : nmax + 3 * (size_t)c;
+    memcpy(lo, a, 12); memcpy(hi, b, 12);
+}
+
+/* bmin/bmax: n*3 primitive boxes in slot order.  Outputs as drb_scene_lbvh: keys[n] and order[n] sorted;
+ * parent/left/right[n-1]; node_min/node_max[(n-1)*3]; scene_bounds[6].  Returns the tree height. */
+int lbvh_host_build(const float* bmin, const float* bmax, int n, uint64_t* keys, int32_t* order, int32_t* parent, int32_t* left,
+                    int32_t* right, float* node_min, float* node_max, float* scene_bounds)
+{
+    if (n <= 0) return 0;
+    float slo[3] = { bmin[0], bmin[1], bmin[2] }, shi[3] = { bmax[0], bmax[1], bmax[2] };
+    for (int i = 1; i < n; i++)
+        for (int a = 0; a < 3; a++) {
+            if (bmin[3 * i + a] < slo[a]) slo[a] = bmin[3 * i + a];
+            if (bmax[3 * i + a] > shi[a]) shi[a] = bmax[3 * i + a];
+        }
+    if (scene_bounds) { memcpy(scene_bounds, slo, 12); memcpy(scene_bounds + 3, shi, 12); }
+    kv* tmp = (kv*)malloc(sizeof(kv) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        uint32_t q[3];
+        for (int a = 0; a < 3; a++) {
+            float c = (bmin[3 * i + a] + bmax[3 * i + a]) * 0.5f;
+            float ext = shi[a] - slo[a];
+            if (!(ext > 0.0f)) ext = 1.0f;
+            float x = ((c - slo[a]) / ext) * 2097152.0f;
+            x = fminf(fmaxf(x, 0.0f), 2097151.0f);
+            q[a] = (uint32_t)x;
+        }
+        tmp[i].key = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+        tmp[i].slot = i;
+    }
+    qsort(tmp, (size_t)n, sizeof(kv), kv_cmp);
+    for (int i = 0; i < n; i++) { keys[i] = tmp[i].key; order[i] = tmp[i].slot; }
+    free(tmp);
+    if (n == 1) return 1;
+
+    int32_t* leaf_parent = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    for (int i = 0; i < n - 1; i++) {
+        int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+        int dmin = delta(keys, n, i, i - d);
+        int lmax = 2;
+        while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+        int l = 0;
+        for (int t = lmax >> 1; t >= 1; t >>= 1)
+            if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+        int j = i + l * d;
+        int dnode = delta(keys, n, i, j);
+        int s = 0;
+        for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+            if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+            if (t <= 1) break;
+        }
+        int gamma = i + s * d + (d < 0 ? d : 0);
+        int lo = i < j ? i : j, hi = i < j ? j : i;
+        int lc = (lo == gamma) ? ~gamma : gamma;
+        int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+        left[i] = lc; right[i] = rc;
+        if (lc < 0) leaf_parent[gamma] = i; else parent[gamma] = i;
+        if (rc < 0) leaf_parent[gamma + 1] = i; else parent[gamma + 1] = i;
+    }
+    parent[0] = -1;
+
+    /* leaf boxes in sorted order */
+    float* lmin = (float*)malloc(12 * (size_t)n); float* lmax = (float*)malloc(12 * (size_t)n);
+    for (int k = 0; k < n; k++) { memcpy(lmin + 3 * k, bmin + 3 * (size_t)order[k], 12); memcpy(lmax + 3 * k, bmax + 3 * (size_t)order[k], 12); }
+    /* bottom-up: a node is ready when both children are; process by repeated leaf climbs like the device */
+    int* visits = (int*)calloc((size_t)(n - 1), sizeof(int));
+    int* height = (int*)calloc((size_t)(n - 1), sizeof(int));
+    int tree_height = 0;
+    for (int k = 0; k < n; k++) {
+        int node = leaf_parent[k];
+        while (node >= 0) {
+            if (visits[node]++ == 0) break;
+            float a0[3], a1[3], b0[3], b1[3];
+            node_box(left[node], lmin, lmax, node_min, node_max, a0, a1);
+            node_box(right[node], lmin, lmax, node_min, node_max, b0, b1);
+            for (int a = 0; a < 3; a++) { node_min[3 * node + a] = fminf(a0[a], b0[a]); node_max[3 * node + a] = fmaxf(a1[a], b1[a]); }
+            int hl = left[node] < 0 ? 0 : height[left[node]], hr = right[node] < 0 ? 0 : height[right[node]];
+            height[node] = (hl > hr ? hl : hr) + 1;
+            if (node == 0) tree_height = height[0];
+            node = parent[node];
+        }
+    }
+    free(visits); free(height); free(lmin); free(lmax); free(leaf_parent);
+    return tree_height;
+}

@@ -9,7 +9,7 @@
  *
  *   word(seed, x, y, sample, n) = Philox4x32-10(key = {seed.lo, seed.hi},
  *                                  ctr = {x, y, sample, n >> 2})[n & 3]
- *   uniform(n) = ((word >> 8) + 0.5) * 2^-24          in (0, 1), 24-bit grid
+ *   uniform(n) = float((word >> 8) + 0.5f) * 2^-24   in (0, 1] (float rounding of k + 0.5 for k >= 2^23)
  *
  * n counts the draws of one (pixel, sample) path in call order, exactly the
  * order the reference consumes them.  The product has its
@@ -59,7 +59,7 @@ static inline uint32_t orc_rng_word(orc_rng* r)
     return r->buf[n & 3u];
 }
 
-/* (0,1) on a 24-bit grid: exactly representable in float, and 2u-1 is too */
+/* (0,1] on the 2^-25 grid, like curand_uniform_double's range; 2u-1 is exact in float */
 static inline float orc_rng_uniform(orc_rng* r)
 {
     return ((float)(orc_rng_word(r) >> 8) + 0.5f) * (1.0f / 16777216.0f);

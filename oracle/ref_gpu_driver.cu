@@ -83,7 +83,8 @@ int refgpu_load(const char* rts_path, const char* tex_dir)
     g_nodes = new bvh[bvhnum];
     g_tex = new cudaTextureObject_t[texnum > 0 ? texnum : 1];
     readtextures(g_tex, g_texpaths);
-    build_bvh(g_nodes, g_objs);
+    if (nanum[0] - 1 >= 2) build_bvh(g_nodes, g_objs);     /* see ref_host_api.inc: fewer than two objects never terminates */
+    else return -4;
     nbvhnumnum[0] = bvhnum;
     cudaMemcpyToSymbol(anum, &nanum[0], sizeof(int), 0, cudaMemcpyHostToDevice);
     cudaMemcpyToSymbol(dbvhnumnum, &nbvhnumnum[0], sizeof(int), 0, cudaMemcpyHostToDevice);

@@ -1,0 +1,64 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/dogeray_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dogeray_b200 as drb
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dogeray_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(drb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    lib = ctypes.CDLL(drb.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libdogeray_b200.so does not export %s" % n
+    assert sorted(drb.EXPORTED_SYMBOLS) == names
+
+
+def test_abi_version_and_struct_sizes():
+    assert drb._lib.drb_abi_version() == 1
+    assert ctypes.sizeof(drb.Settings) == 60
+    assert drb.OBJECT_DTYPE.itemsize == 156
+    assert ctypes.sizeof(drb.Opts) == 32
+    assert ctypes.sizeof(drb.Stats) == 32
+
+
+def test_default_settings_are_reference_defaults():
+    s = drb.default_settings()      # raygpu/kernel.cu:29-30, 119-132
+    assert list(s.cam) == [0, 0, 2] and list(s.look) == [0, 0, 0]
+    assert s.aperture == np.float32(0.01) and s.focus == 3 and s.fov == 45
+    assert s.max_depth == 50 and s.spp == 1 and s.bg_intensity == 1 and s.backtex == -1
+    assert (s.width, s.height) == (1280, 720)
+
+
+def test_no_cpu_fallback_without_device(tmp_path):
+    if drb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    objs = drb.make_objects(1)
+    hs = drb.HostScene.from_objects(objs)
+    with pytest.raises(drb.DogerayError) as e:
+        drb.Scene.from_host(hs)
+    assert e.value.status == drb.ERR_CUDA
+    assert "no CPU path" in str(e.value)
+
+
+def test_error_codes():
+    with pytest.raises(drb.DogerayError) as e:
+        drb.HostScene.load("/nonexistent/scene.rts")
+    assert e.value.status == drb.ERR_IO
+    with pytest.raises(drb.DogerayError) as e:
+        drb.HostScene.parse(b"1,2,abc,2,0,0,0\n")
+    assert e.value.status == drb.ERR_PARSE and "column 2" in str(e.value)
+    with pytest.raises(drb.DogerayError) as e:
+        drb.read_ppm("/nonexistent.ppm")
+    assert e.value.status == drb.ERR_IO

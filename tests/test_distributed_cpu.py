@@ -1,0 +1,72 @@
+"""The N>1 path on CPU: world_size-2 gloo, samples sharded, one reduce -- with the C oracle standing in
+for the GPU renderer (the sharding / reduce logic is the code under test, not the oracle)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from dogeray_b200.distributed import shard_samples
+from conftest import ROOT
+
+
+def test_shard_samples_partitions_exactly():
+    for spp in (0, 1, 7, 8, 256, 1023):
+        for world in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(world):
+                b, c = shard_samples(spp, r, world, base=5)
+                got += list(range(b, b + c))
+            assert got == list(range(5, 5 + spp))
+            counts = [shard_samples(spp, r, world)[1] for r in range(world)]
+            assert max(counts) - min(counts) <= 1
+    with pytest.raises(ValueError):
+        shard_samples(4, 2, 2)
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import dogeray_b200 as drb
+from dogeray_b200 import synth
+from dogeray_b200.distributed import init_from_env, render_sharded
+from oracle import restated
+
+rank, world = init_from_env("gloo")
+objs, st = synth.heightfield_scene(n=10, width=24, height=16, spp=5, max_depth=4)
+path = os.path.join(sys.argv[2], "s%d.rts" % rank)
+drb.write_rts(path, st, objs)
+r = restated.Restated(path)
+
+def render(base, count):
+    s = st.replace(spp=max(count, 1))
+    r.apply(s); r.set_seed(3)
+    f, _, _ = r.frame(1, base, threads=1)                      # 255 * mean over `count` samples, (W,H,3)
+    return torch.from_numpy((f.astype(np.float64) * count / 255.0).astype(np.float32)) if count else torch.zeros(st.width, st.height, 3)
+
+acc, count = render_sharded(render, st.spp, rank, world)
+if rank == 0:
+    r.apply(st); r.set_seed(3)
+    full, _, _ = r.frame(1, 0, threads=1)
+    got = acc.numpy() / st.spp * 255.0
+    err = float(np.abs(got - full).max())
+    print("MAXERR %g" % err)
+    assert err < 2e-3, err
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sample_sharding(tmp_path):
+    import subprocess
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script), ROOT, str(tmp_path)]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "MAXERR" in p.stdout

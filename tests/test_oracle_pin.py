@@ -1,0 +1,120 @@
+"""Pins the plain-C restatement (oracle/dogeray_oracle.c) to the reference: against oracle/_ref (the
+reference's own kernel.cu compiled for the host) where it is present, and against the committed golden
+vectors that were generated from oracle/_ref (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import dogeray_b200 as drb
+from dogeray_b200 import synth
+from oracle import restated
+from conftest import SAMPLES, needs_ref, sample
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+PIN_SCENES = [("cube.rts", {}), ("mats.rts", {}), ("glass.rts", {"max_depth": 8}), ("bolter2.blend.rts", {}), ("rough.blend.rts", {}),
+              ("gloss.rts", {}), ("uv2.rts", {}), ("lots.rts", {}), ("cow.rts", {}), ("smoothdiff.rts", {}), ("glasstest.rts", {"max_depth": 8}),
+              ("SPERSSSSS.rts", {})]
+
+
+def settings_from_vector(v):
+    st = drb.default_settings()
+    st.cam[:] = v[0:3]; st.aperture = v[3]; st.look[:] = v[4:7]; st.focus = v[7]
+    st.fov, st.max_depth, st.spp = int(v[8]), int(v[9]), int(v[10])
+    st.bg_intensity = v[11]; st.backtex = int(v[12]); st.width, st.height = int(v[13]), int(v[14])
+    return st
+
+
+@needs_ref
+@pytest.mark.parametrize("name,over", PIN_SCENES)
+def test_restatement_equals_reference(ref, name, over):
+    ref.load(sample(name), SAMPLES)
+    r = restated.Restated(sample(name), SAMPLES)
+    assert r.num_objects == ref.num_objects and r.num_nodes == ref.num_nodes
+    s = ref.get_settings()
+    assert np.array_equal(s, r.get_settings())
+    s[13], s[14], s[10], s[9] = 48, 40, 2, over.get("max_depth", 5)
+    ref.set_settings(s); r.set_settings(s); ref.set_seed(9); r.set_seed(9)
+    f1, i1, rays1 = ref.frame()
+    f2, i2, rays2 = r.frame()
+    assert rays1 == rays2
+    assert np.array_equal(f1, f2) and np.array_equal(i1, i2)            # bit-identical float frames
+    o, d = r.primary_rays(0)
+    ids1, t1 = ref.hit(o, d)
+    ids2, t2 = r.hit(o, d)
+    assert np.array_equal(ids1, ids2) and np.array_equal(t1, t2)
+    ids3, t3 = r.hit_brute(o, d)                                        # the tree never changes the answer
+    same = ids3 == ids1
+    assert np.array_equal(t3[same], t1[same])
+    for k in np.flatnonzero(~same):                                     # only exact-t ties may pick another object
+        assert t3[k] == t1[k]
+
+
+@needs_ref
+def test_frame_divisor_and_sample_base(ref):
+    ref.load(sample("mats.rts"), SAMPLES)
+    r = restated.Restated(sample("mats.rts"), SAMPLES)
+    s = ref.get_settings(); s[13], s[14], s[10], s[9] = 72, 50, 2, 4        # 50 is not a multiple of 8: partial blocks dropped
+    for div, base in ((1, 0), (2, 0), (1, 7)):
+        ref.set_settings(s); r.set_settings(s); ref.set_seed(1); r.set_seed(1)
+        f1, i1, _ = ref.frame(div, base)
+        f2, i2, _ = r.frame(div, base)
+        assert np.array_equal(f1, f2) and np.array_equal(i1, i2)
+        assert (i1[72 // div // 8 * 8:, :, :] == 0).all()
+
+
+def _check_golden(g, r):
+    st = settings_from_vector(g["settings"])
+    r.apply(st); r.set_seed(int(g["seed"]))
+    o, d = r.primary_rays(0)
+    assert np.array_equal(o, g["origins"]) and np.array_equal(d, g["dirs"])
+    ids, t = r.hit(o, d)
+    assert np.array_equal(ids, g["ids"]) and np.array_equal(t, g["t"])
+    f, i, rays = r.frame()
+    assert rays == int(g["rays"]) and np.array_equal(f, g["frame"]) and np.array_equal(i, g["frame_i"])
+
+
+def test_restatement_against_golden_synthetic(tmp_path):
+    """runs everywhere: the scene is regenerated, the expected numbers came from the reference"""
+    g = np.load(os.path.join(GOLDEN, "synth_heightfield.npz"))
+    objs, st = synth.heightfield_scene(n=24, width=48, height=40, spp=3, max_depth=5)
+    p = str(tmp_path / "hf.rts")
+    drb.write_rts(p, st, objs)
+    _check_golden(g, restated.Restated(p))
+
+
+@needs_ref
+def test_restatement_against_golden_cube():
+    g = np.load(os.path.join(GOLDEN, "cube_frame.npz"))
+    _check_golden(g, restated.Restated(sample("cube.rts")))
+
+
+def test_host_lbvh_is_a_valid_tree():
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 3, 17, 1000):
+        c = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+        if n == 17:
+            c[:] = c[0]                                                  # all keys tie: falls back to positions
+        e = rng.uniform(0.01, 0.3, (n, 3)).astype(np.float32)
+        t = restated.lbvh_host(c - e, c + e)
+        assert sorted(t["order"].tolist()) == list(range(n))
+        assert (np.diff(t["keys"].astype(np.int64)) >= 0).all()
+        if n == 1:
+            continue
+        seen_leaf = np.zeros(n, int); seen_node = np.zeros(n - 1, int)
+        stack = [0]
+        while stack:
+            k = stack.pop()
+            seen_node[k] += 1
+            for ch in (t["left"][k], t["right"][k]):
+                if ch < 0:
+                    seen_leaf[~ch] += 1
+                    lo, hi = (c - e)[t["order"][~ch]], (c + e)[t["order"][~ch]]
+                else:
+                    assert t["parent"][ch] == k
+                    stack.append(int(ch))
+                    lo, hi = t["node_min"][ch], t["node_max"][ch]
+                assert (t["node_min"][k] <= lo).all() and (t["node_max"][k] >= hi).all()
+        assert (seen_leaf == 1).all() and (seen_node == 1).all() and t["parent"][0] == -1
+        assert np.array_equal(t["node_min"][0], (c - e).min(0)) and np.array_equal(t["node_max"][0], (c + e).max(0))
