@@ -29,6 +29,7 @@ _lib = C.CDLL(LIB_PATH)
 
 OK, ERR_ARG, ERR_IO, ERR_PARSE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 FLAG_ACCUMULATE = 1
+BUILD_LBVH_ONLY = 1
 
 
 class DogerayError(RuntimeError):
@@ -97,7 +98,7 @@ class Stats(C.Structure):
 class BuildInfo(C.Structure):
     _fields_ = [
         ("nprims", C.c_int64), ("nnodes", C.c_int64), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3),
-        ("upload_ms", C.c_float), ("build_ms", C.c_float), ("max_depth", C.c_int32),
+        ("upload_ms", C.c_float), ("build_ms", C.c_float), ("max_depth", C.c_int32), ("rebuild_iterations", C.c_int32),
     ]
 
 
@@ -125,6 +126,8 @@ _sig("drb_host_scene_num_skipped", _i64, _vp)
 _sig("drb_rts_write", _i, _cp, C.POINTER(Settings), _vp, _i64, C.POINTER(_cp), _i, _cp)
 _sig("drb_settings_default", None, C.POINTER(Settings))
 _sig("drb_scene_create", _i, _vp, _i, _pp)
+_sig("drb_scene_create_ex", _i, _vp, _i, _u32, _pp)
+_sig("drb_scene_tree", _i, _vp, _vp, _vp, _vp, _vp)
 _sig("drb_scene_load", _i, _cp, _cp, _i, _pp)
 _sig("drb_scene_free", None, _vp)
 _sig("drb_scene_settings", _i, _vp, C.POINTER(Settings))
@@ -153,7 +156,7 @@ EXPORTED_SYMBOLS = [
     "drb_host_scene_load", "drb_host_scene_parse", "drb_host_scene_create", "drb_host_scene_free",
     "drb_host_scene_num_objects", "drb_host_scene_objects", "drb_host_scene_settings",
     "drb_host_scene_num_textures", "drb_host_scene_texture_path", "drb_host_scene_num_skipped",
-    "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_load", "drb_scene_free",
+    "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_create_ex", "drb_scene_tree", "drb_scene_load", "drb_scene_free",
     "drb_scene_settings", "drb_scene_num_prims", "drb_scene_num_objects", "drb_scene_build_info",
     "drb_scene_lbvh", "drb_opts_default", "drb_render_device", "drb_render", "drb_frame_i3",
     "drb_trace_ids", "drb_primary_rays", "drb_tonemap", "drb_tonemap_device", "drb_write_bmp",
@@ -294,9 +297,9 @@ class Scene:
         return cls(h)
 
     @classmethod
-    def from_host(cls, hs: HostScene, device: int = 0) -> "Scene":
+    def from_host(cls, hs: HostScene, device: int = 0, build_flags: int = 0) -> "Scene":
         h = C.c_void_p()
-        _check(_lib.drb_scene_create(hs.handle, device, C.byref(h)))
+        _check(_lib.drb_scene_create_ex(hs.handle, device, build_flags, C.byref(h)))
         return cls(h)
 
     def close(self):
@@ -340,6 +343,14 @@ class Scene:
         _check(_lib.drb_scene_lbvh(self._h, keys.ctypes.data, order.ctypes.data, parent.ctypes.data, left.ctypes.data,
                                    right.ctypes.data, nmin.ctypes.data, nmax.ctypes.data))
         return dict(keys=keys, order=order, parent=parent, left=left, right=right, node_min=nmin, node_max=nmax)
+
+    def tree(self):
+        """The hierarchy the traversal nodes were emitted from (root = node 0): left, right, node_min, node_max."""
+        ni = max(self.num_prims - 1, 0)
+        left = np.zeros(ni, np.int32); right = np.zeros(ni, np.int32)
+        nmin = np.zeros((ni, 3), np.float32); nmax = np.zeros((ni, 3), np.float32)
+        _check(_lib.drb_scene_tree(self._h, left.ctypes.data, right.ctypes.data, nmin.ctypes.data, nmax.ctypes.data))
+        return dict(left=left, right=right, node_min=nmin, node_max=nmax)
 
     @staticmethod
     def _opts(seed=0, sample_base=0, sample_count=0, batch_paths=0, flags=0, stream=None) -> Opts:

@@ -61,8 +61,17 @@ struct LbvhDebug {              // integer outputs of the build, kept for drb_sc
     float4* node_max = nullptr; // n-1
 };
 
+struct FinalTree {              // the hierarchy the nodes were emitted from (root = node 0), for drb_scene_tree
+    int32_t* left = nullptr;    // n-1
+    int32_t* right = nullptr;   // n-1
+    float4* node_min = nullptr; // n-1
+    float4* node_max = nullptr; // n-1
+};
+
 struct drb_scene {
     int device = 0;
+    uint32_t build_flags = 0;
+    FinalTree tree;
     drb_settings settings;
     int64_t nobjects = 0;       // object lines
     int64_t nprims = 0;         // renderable primitives (in the tree)

@@ -11,7 +11,10 @@ struct drb_host_scene {
     std::vector<std::string> tex_paths;   // candidate texture files, sorted
     int64_t skipped = 0;                  // lines that were not turned into objects
     std::string first_warning;
+    mutable bool pinned = false;          // objects[] page-locked by the first drb_scene_create (scene.cu)
 };
+// releases the page lock, if any (defined in scene.cu, the only TU that talks to CUDA about it)
+void drb_host_scene_unpin(drb_host_scene* hs);
 
 // thread-local last-error string behind drb_last_error()
 void drb_set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));

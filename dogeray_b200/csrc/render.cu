@@ -622,15 +622,17 @@ int ensure_buffers(drb_scene* s, size_t slots)
     drb_render_buffers_free(s);
     s->rb = rb = new RenderBuffers();
     Queues& q = rb->q;
+    cudaStream_t st = s->stream;
     for (int k = 0; k < 2; ++k) {
-        DRB_CUDA(cudaMalloc((void**)&q.ray_o[k], slots * sizeof(float4)));
-        DRB_CUDA(cudaMalloc((void**)&q.ray_d[k], slots * sizeof(float4)));
-        DRB_CUDA(cudaMalloc((void**)&q.thr[k], slots * sizeof(float4)));
+        DRB_CUDA(cudaMallocAsync((void**)&q.ray_o[k], slots * sizeof(float4), st));
+        DRB_CUDA(cudaMallocAsync((void**)&q.ray_d[k], slots * sizeof(float4), st));
+        DRB_CUDA(cudaMallocAsync((void**)&q.thr[k], slots * sizeof(float4), st));
     }
-    DRB_CUDA(cudaMalloc((void**)&q.hit, slots * sizeof(uint2)));
-    DRB_CUDA(cudaMalloc((void**)&q.contrib, slots * sizeof(float4)));
-    DRB_CUDA(cudaMalloc((void**)&q.counters, CNT_WORDS * sizeof(uint32_t)));
-    DRB_CUDA(cudaMemset(q.counters, 0, CNT_WORDS * sizeof(uint32_t)));
+    DRB_CUDA(cudaMallocAsync((void**)&q.hit, slots * sizeof(uint2), st));
+    DRB_CUDA(cudaMallocAsync((void**)&q.contrib, slots * sizeof(float4), st));
+    DRB_CUDA(cudaMallocAsync((void**)&q.counters, CNT_WORDS * sizeof(uint32_t), st));
+    DRB_CUDA(cudaMemsetAsync(q.counters, 0, CNT_WORDS * sizeof(uint32_t), st));
+    DRB_CUDA(cudaStreamSynchronize(st));             // the buffers may be used from a caller-provided stream next
     rb->capacity = slots;
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
@@ -756,8 +758,10 @@ void drb_render_buffers_free(drb_scene* s)
 {
     if (!s || !s->rb) return;
     Queues& q = s->rb->q;
-    for (int k = 0; k < 2; ++k) { cudaFree(q.ray_o[k]); cudaFree(q.ray_d[k]); cudaFree(q.thr[k]); }
-    cudaFree(q.hit); cudaFree(q.contrib); cudaFree(q.counters);
+    cudaStream_t st = s->stream;
+    cudaDeviceSynchronize();                          // renders may have run on caller streams
+    for (int k = 0; k < 2; ++k) { cudaFreeAsync(q.ray_o[k], st); cudaFreeAsync(q.ray_d[k], st); cudaFreeAsync(q.thr[k], st); }
+    cudaFreeAsync(q.hit, st); cudaFreeAsync(q.contrib, st); cudaFreeAsync(q.counters, st);
     delete s->rb;
     s->rb = nullptr;
 }
@@ -784,9 +788,9 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
     DRB_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)settings->width * settings->height * 3;
     float* d = nullptr;
-    DRB_CUDA(cudaMalloc((void**)&d, n * sizeof(float)));
     drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
+    DRB_CUDA(cudaMallocAsync((void**)&d, n * sizeof(float), stream));
     int rc = DRB_OK;
     if (o.flags & DRB_FLAG_ACCUMULATE) {
         if (cudaMemcpyAsync(d, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DRB_ERR_CUDA;
@@ -797,7 +801,7 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) { drb_set_error("download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
     }
-    cudaFree(d);
+    cudaFreeAsync(d, stream);
     return rc;
 }
 
@@ -815,8 +819,8 @@ int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opt
     const uint32_t spp = o.sample_count ? o.sample_count : (uint32_t)std::max(settings->spp, 0);
     float* d_acc = nullptr; int32_t* d_out = nullptr;
     const size_t nfull = (size_t)settings->width * settings->height * 3;
-    DRB_CUDA(cudaMalloc((void**)&d_acc, (size_t)W * H * 3 * sizeof(float)));
-    if (cudaMalloc((void**)&d_out, nfull * sizeof(int32_t)) != cudaSuccess) { cudaFree(d_acc); drb_set_error("out of device memory"); return DRB_ERR_NOMEM; }
+    DRB_CUDA(cudaMallocAsync((void**)&d_acc, (size_t)W * H * 3 * sizeof(float), stream));
+    if (cudaMallocAsync((void**)&d_out, nfull * sizeof(int32_t), stream) != cudaSuccess) { cudaFreeAsync(d_acc, stream); drb_set_error("out of device memory"); return DRB_ERR_NOMEM; }
     int rc = DRB_OK;
     {
         // entries outside the launched grid stay as the caller left them
@@ -832,7 +836,7 @@ int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opt
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) { drb_set_error("frame download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
     }
-    cudaFree(d_acc); cudaFree(d_out);
+    cudaFreeAsync(d_acc, stream); cudaFreeAsync(d_out, stream);
     return rc;
 }
 
@@ -847,10 +851,10 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     Queues q = rb->q;
     cudaStream_t stream = s->stream;
     float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int32_t* d_ids = nullptr;
-    DRB_CUDA(cudaMalloc((void**)&d_o, (size_t)n * 12));
-    DRB_CUDA(cudaMalloc((void**)&d_d, (size_t)n * 12));
-    DRB_CUDA(cudaMalloc((void**)&d_t, (size_t)n * 4));
-    DRB_CUDA(cudaMalloc((void**)&d_ids, (size_t)n * 4));
+    DRB_CUDA(cudaMallocAsync((void**)&d_o, (size_t)n * 12, stream));
+    DRB_CUDA(cudaMallocAsync((void**)&d_d, (size_t)n * 12, stream));
+    DRB_CUDA(cudaMallocAsync((void**)&d_t, (size_t)n * 4, stream));
+    DRB_CUDA(cudaMallocAsync((void**)&d_ids, (size_t)n * 4, stream));
     cudaMemcpyAsync(d_o, o3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_d, d3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
     const uint32_t nn = (uint32_t)n;
@@ -862,7 +866,7 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     if (t) cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_ids);
+    cudaFreeAsync(d_o, stream); cudaFreeAsync(d_d, stream); cudaFreeAsync(d_t, stream); cudaFreeAsync(d_ids, stream);
     if (e != cudaSuccess) { drb_set_error("drb_trace_ids: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
     return DRB_OK;
 }
@@ -883,15 +887,15 @@ int drb_primary_rays(drb_scene* s, const drb_settings* settings, const drb_opts*
     cudaStream_t stream = s->stream;
     const size_t n = (size_t)W * H * 3;
     float *d_o = nullptr, *d_d = nullptr;
-    DRB_CUDA(cudaMalloc((void**)&d_o, n * 4));
-    DRB_CUDA(cudaMalloc((void**)&d_d, n * 4));
+    DRB_CUDA(cudaMallocAsync((void**)&d_o, n * 4, stream));
+    DRB_CUDA(cudaMallocAsync((void**)&d_d, n * 4, stream));
     k_generate<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q);
     k_store_rays<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q, d_o, d_d);
     cudaMemcpyAsync(o3, d_o, n * 4, cudaMemcpyDeviceToHost, stream);
     cudaMemcpyAsync(d3, d_d, n * 4, cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_o); cudaFree(d_d);
+    cudaFreeAsync(d_o, stream); cudaFreeAsync(d_d, stream);
     if (e != cudaSuccess) { drb_set_error("drb_primary_rays: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
     return DRB_OK;
 }

@@ -368,7 +368,7 @@ int drb_host_scene_create(const drb_settings* settings, const drb_object* object
     return DRB_OK;
 }
 
-void drb_host_scene_free(drb_host_scene* hs) { delete hs; }
+void drb_host_scene_free(drb_host_scene* hs) { if (hs) { drb_host_scene_unpin(hs); delete hs; } }
 int64_t drb_host_scene_num_objects(const drb_host_scene* hs) { return hs ? (int64_t)hs->objects.size() : 0; }
 const drb_object* drb_host_scene_objects(const drb_host_scene* hs) { return hs && !hs->objects.empty() ? hs->objects.data() : nullptr; }
 int drb_host_scene_settings(const drb_host_scene* hs, drb_settings* out)

@@ -254,6 +254,114 @@ __global__ void k_refit(int n, const float4* __restrict__ lmin, const float4* __
     }
 }
 
+
+// ---- SAH-guided rebuild of the hierarchy: agglomerative clustering over the Morton order ---------------
+// (Meister & Bittner, "Parallel Locally-Ordered Clustering for BVH Construction", TVCG 2018.)
+// The Karras tree above splits where the Morton prefix changes, which ignores surface area; traversal
+// of it visits ~1.5x more nodes than a SAH-quality tree.  Starting from the same sorted leaves, every
+// cluster looks `radius` positions left and right for the neighbour whose union box has the smallest
+// surface area; mutually nearest pairs merge into a new node, the survivors are compacted in order, and
+// the process repeats until one cluster is left.  All steps are deterministic (ties go to the lower
+// position; node ids come from a prefix sum, not from atomics), so oracle/lbvh_host.c reproduces the
+// topology bit for bit.
+constexpr int kPlocRadius = 16;
+
+__device__ __forceinline__ float union_half_area(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi)
+{
+    const float ex = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
+    const float ey = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y);
+    const float ez = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return ex * ey + ey * ez + ez * ex;
+}
+
+__global__ void k_ploc_nn(int n, const float4* __restrict__ cmin, const float4* __restrict__ cmax, int32_t* __restrict__ nn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 lo = cmin[i], hi = cmax[i];
+    float best = 3.4e38f; int bj = -1;
+    const int j0 = max(0, i - kPlocRadius), j1 = min(n - 1, i + kPlocRadius);
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float a = union_half_area(lo, hi, cmin[j], cmax[j]);
+        if (a < best) { best = a; bj = j; }
+    }
+    if (bj < 0) bj = (i ^ 1) < n ? (i ^ 1) : i - 1;        // non-finite boxes: pair neighbours so the loop still ends
+    nn[i] = bj;
+}
+
+// low word: cluster survives at this position; high word: it is the lower half of a merging pair
+__global__ void k_ploc_flag(int n, const int32_t* __restrict__ nn, unsigned long long* __restrict__ f)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = nn[i];
+    const bool mutual = j >= 0 && j < n && nn[j] == i;
+    const unsigned long long valid = !(mutual && i > j), merge = (mutual && i < j);
+    f[i] = valid | (merge << 32);
+}
+
+__global__ void k_ploc_emit(int n, const int32_t* __restrict__ nn, const unsigned long long* __restrict__ f, const unsigned long long* __restrict__ sc,
+                            const int32_t* __restrict__ cid, const float4* __restrict__ cmin, const float4* __restrict__ cmax,
+                            int32_t* __restrict__ cid_o, float4* __restrict__ cmin_o, float4* __restrict__ cmax_o, int node_base,
+                            int32_t* __restrict__ left, int32_t* __restrict__ right, float4* __restrict__ node_min, float4* __restrict__ node_max,
+                            int* __restrict__ totals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long fi = f[i], si = sc[i];
+    if (i == n - 1) { totals[0] = (int)(uint32_t)si + (int)(fi & 1ull); totals[1] = (int)(si >> 32) + (int)(fi >> 32); }
+    if (!(fi & 1ull)) return;
+    const int pos = (int)(uint32_t)si;
+    if (fi >> 32) {
+        const int j = nn[i];
+        const int node = node_base + (int)(si >> 32);
+        const int a = cid[i], b = cid[j];
+        const float4 alo = cmin[i], ahi = cmax[i], blo = cmin[j], bhi = cmax[j];
+        const int ha = a < 0 ? 0 : __float_as_int(alo.w), hb = b < 0 ? 0 : __float_as_int(blo.w);
+        const float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float(max(ha, hb) + 1));
+        const float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+        left[node] = a; right[node] = b;
+        node_min[node] = lo; node_max[node] = hi;
+        cid_o[pos] = node; cmin_o[pos] = lo; cmax_o[pos] = hi;
+    } else {
+        cid_o[pos] = cid[i]; cmin_o[pos] = cmin[i]; cmax_o[pos] = cmax[i];
+    }
+}
+
+__global__ void k_ploc_init(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, int32_t* __restrict__ cid,
+                            float4* __restrict__ cmin, float4* __restrict__ cmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cid[i] = ~i;
+    float4 lo = lmin[i]; lo.w = 0.f;
+    cmin[i] = lo; cmax[i] = lmax[i];
+}
+
+// final labelling: node created k-th becomes (n - 2) - k, so the root is node 0 and parents precede children
+__global__ void k_emit_relabelled(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
+                                  const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
+                                  BvhNode* __restrict__ nodes, int32_t* __restrict__ fleft, int32_t* __restrict__ fright,
+                                  float4* __restrict__ fmin, float4* __restrict__ fmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int lc = left[i], rc = right[i];
+    const float4 a0 = lc < 0 ? lmin[~lc] : node_min[lc], a1 = lc < 0 ? lmax[~lc] : node_max[lc];
+    const float4 b0 = rc < 0 ? lmin[~rc] : node_min[rc], b1 = rc < 0 ? lmax[~rc] : node_max[rc];
+    const int dst = (n - 2) - i;
+    const int flc = lc < 0 ? lc : (n - 2) - lc, frc = rc < 0 ? rc : (n - 2) - rc;
+    BvhNode nd;
+    nd.c0xy = make_float4(a0.x, a1.x, a0.y, a1.y);
+    nd.c1xy = make_float4(b0.x, b1.x, b0.y, b1.y);
+    nd.cz = make_float4(a0.z, a1.z, b0.z, b1.z);
+    nd.link = make_int4(flc, frc, 0, 0);
+    nodes[dst] = nd;
+    fleft[dst] = flc; fright[dst] = frc;
+    fmin[dst] = node_min[i]; fmax[dst] = node_max[i];
+}
+
 __global__ void k_emit_nodes(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
                              const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
                              BvhNode* __restrict__ nodes)
@@ -283,31 +391,46 @@ __global__ void k_emit_single(const float4* __restrict__ lmin, const float4* __r
     nodes[0] = nd;
 }
 
-template <typename T> int dev_alloc(T** p, size_t count)
+// All device memory comes from the device's default stream-ordered pool with its release threshold
+// raised to "never": a scene that is created, rendered and freed every frame (the reference's
+// CudaStarter pattern, kernel.cu:2604-2665) then recycles the same blocks instead of paying
+// cudaMalloc/cudaFree (hundreds of ms per frame for the ~3 GB a 1 M-triangle 1080p frame uses).
+template <typename T> int dev_alloc(T** p, size_t count, cudaStream_t st)
 {
     *p = nullptr;
     if (count == 0) count = 1;
-    DRB_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    DRB_CUDA(cudaMallocAsync((void**)p, count * sizeof(T), st));
     return DRB_OK;
 }
 
 struct Scratch {
+    cudaStream_t st;
     std::vector<void*> ptrs;
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
     template <typename T> int alloc(T** p, size_t count)
     {
-        int rc = dev_alloc(p, count);
+        int rc = dev_alloc(p, count, st);
         if (rc == DRB_OK) ptrs.push_back(*p);
         return rc;
     }
 };
+
+int retain_pool(int device)
+{
+    cudaMemPool_t pool;
+    DRB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    DRB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    return DRB_OK;
+}
 
 int build_tree(drb_scene* s, const drb_host_scene* hs)
 {
     const int64_t nobj = (int64_t)hs->objects.size();
     if (nobj >= (1ll << 31) - 8) { drb_set_error("too many objects (%lld)", (long long)nobj); return DRB_ERR_UNSUPPORTED; }
     cudaStream_t st = s->stream;
-    Scratch tmp;
+    Scratch tmp(st);
     cudaEvent_t e0, e1, e2;
     DRB_CUDA(cudaEventCreate(&e0)); DRB_CUDA(cudaEventCreate(&e1)); DRB_CUDA(cudaEventCreate(&e2));
     DRB_CUDA(cudaEventRecord(e0, st));
@@ -341,18 +464,22 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
     memset(&s->info, 0, sizeof s->info);
     s->info.nprims = nprims; s->info.nnodes = s->nnodes;
 
-    if (int rc = dev_alloc(&s->prims, (size_t)nprims)) return rc;
-    if (int rc = dev_alloc(&s->recs, (size_t)nprims)) return rc;
-    if (int rc = dev_alloc(&s->orig_id, (size_t)nprims)) return rc;
-    if (int rc = dev_alloc(&s->nodes, (size_t)s->nnodes)) return rc;
+    if (int rc = dev_alloc(&s->prims, (size_t)nprims, st)) return rc;
+    if (int rc = dev_alloc(&s->recs, (size_t)nprims, st)) return rc;
+    if (int rc = dev_alloc(&s->orig_id, (size_t)nprims, st)) return rc;
+    if (int rc = dev_alloc(&s->nodes, (size_t)s->nnodes, st)) return rc;
     const size_t nint = nprims > 1 ? (size_t)nprims - 1 : 1;
-    if (int rc = dev_alloc(&s->dbg.keys, (size_t)nprims)) return rc;
-    if (int rc = dev_alloc(&s->dbg.order, (size_t)nprims)) return rc;
-    if (int rc = dev_alloc(&s->dbg.parent, nint)) return rc;
-    if (int rc = dev_alloc(&s->dbg.left, nint)) return rc;
-    if (int rc = dev_alloc(&s->dbg.right, nint)) return rc;
-    if (int rc = dev_alloc(&s->dbg.node_min, nint)) return rc;
-    if (int rc = dev_alloc(&s->dbg.node_max, nint)) return rc;
+    if (int rc = dev_alloc(&s->dbg.keys, (size_t)nprims, st)) return rc;
+    if (int rc = dev_alloc(&s->dbg.order, (size_t)nprims, st)) return rc;
+    if (int rc = dev_alloc(&s->dbg.parent, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->dbg.left, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->dbg.right, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->dbg.node_min, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->dbg.node_max, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->tree.left, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->tree.right, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->tree.node_min, nint, st)) return rc;
+    if (int rc = dev_alloc(&s->tree.node_max, nint, st)) return rc;
 
     int height = 0;
     if (nprims > 0) {
@@ -390,8 +517,57 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
             k_karras<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(s->dbg.keys, nprims, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent);
             k_refit<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent, visits,
                                                        s->dbg.node_min, s->dbg.node_max, d_height);
-            k_emit_nodes<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.node_min, s->dbg.node_max, s->nodes);
-            DRB_CUDA(cudaMemcpyAsync(&height, d_height, 4, cudaMemcpyDeviceToHost, st));
+            if (s->build_flags & DRB_BUILD_LBVH_ONLY) {
+                k_emit_nodes<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.node_min, s->dbg.node_max, s->nodes);
+                DRB_CUDA(cudaMemcpyAsync(s->tree.left, s->dbg.left, nint * 4, cudaMemcpyDeviceToDevice, st));
+                DRB_CUDA(cudaMemcpyAsync(s->tree.right, s->dbg.right, nint * 4, cudaMemcpyDeviceToDevice, st));
+                DRB_CUDA(cudaMemcpyAsync(s->tree.node_min, s->dbg.node_min, nint * 16, cudaMemcpyDeviceToDevice, st));
+                DRB_CUDA(cudaMemcpyAsync(s->tree.node_max, s->dbg.node_max, nint * 16, cudaMemcpyDeviceToDevice, st));
+                DRB_CUDA(cudaMemcpyAsync(&height, d_height, 4, cudaMemcpyDeviceToHost, st));
+            } else {
+                // SAH-guided rebuild over the same sorted leaves
+                int32_t* cid[2]; float4* cmn[2]; float4* cmx[2]; int32_t* nn; unsigned long long *fl, *sc; int* d_tot;
+                int32_t *pl, *pr; float4 *pmin, *pmax;
+                for (int k = 0; k < 2; ++k) {
+                    if (int rc = tmp.alloc(&cid[k], (size_t)nprims)) return rc;
+                    if (int rc = tmp.alloc(&cmn[k], (size_t)nprims)) return rc;
+                    if (int rc = tmp.alloc(&cmx[k], (size_t)nprims)) return rc;
+                }
+                if (int rc = tmp.alloc(&nn, (size_t)nprims)) return rc;
+                if (int rc = tmp.alloc(&fl, (size_t)nprims)) return rc;
+                if (int rc = tmp.alloc(&sc, (size_t)nprims)) return rc;
+                if (int rc = tmp.alloc(&d_tot, 2)) return rc;
+                if (int rc = tmp.alloc(&pl, nint)) return rc;
+                if (int rc = tmp.alloc(&pr, nint)) return rc;
+                if (int rc = tmp.alloc(&pmin, nint)) return rc;
+                if (int rc = tmp.alloc(&pmax, nint)) return rc;
+                size_t pscan_bytes = 0;
+                DRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, pscan_bytes, fl, sc, nprims, st));
+                void* d_pscan = nullptr;
+                if (int rc = tmp.alloc((char**)&d_pscan, pscan_bytes)) return rc;
+                k_ploc_init<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, cid[0], cmn[0], cmx[0]);
+                int n = nprims, node_base = 0, cur = 0, iters = 0;
+                while (n > 1) {
+                    const int g = (n + T - 1) / T;
+                    k_ploc_nn<<<g, T, 0, st>>>(n, cmn[cur], cmx[cur], nn);
+                    k_ploc_flag<<<g, T, 0, st>>>(n, nn, fl);
+                    DRB_CUDA(cub::DeviceScan::ExclusiveSum(d_pscan, pscan_bytes, fl, sc, n, st));
+                    k_ploc_emit<<<g, T, 0, st>>>(n, nn, fl, sc, cid[cur], cmn[cur], cmx[cur], cid[cur ^ 1], cmn[cur ^ 1], cmx[cur ^ 1], node_base,
+                                                 pl, pr, pmin, pmax, d_tot);
+                    int tot[2] = { 0, 0 };
+                    DRB_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
+                    DRB_CUDA(cudaStreamSynchronize(st));
+                    if (tot[1] <= 0 || tot[0] != n - tot[1] || ++iters > 100000) { drb_set_error("hierarchy rebuild made no progress (n=%d, merges=%d)", n, tot[1]); return DRB_ERR_CUDA; }
+                    node_base += tot[1]; n = tot[0]; cur ^= 1;
+                }
+                s->info.rebuild_iterations = iters;
+                k_emit_relabelled<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, pl, pr, pmin, pmax, s->nodes, s->tree.left, s->tree.right,
+                                                                          s->tree.node_min, s->tree.node_max);
+                float4 rootbox;
+                DRB_CUDA(cudaMemcpyAsync(&rootbox, pmin + (nprims - 2), sizeof rootbox, cudaMemcpyDeviceToHost, st));
+                DRB_CUDA(cudaStreamSynchronize(st));
+                memcpy(&height, &rootbox.w, 4);
+            }
         } else {
             k_emit_single<<<1, 1, 0, st>>>(lmin, lmax, s->nodes);
             height = 1;
@@ -436,18 +612,25 @@ int upload_textures(drb_scene* s, const drb_host_scene* hs)
             continue;                                   // the reference loads every .ppm it finds; unused ones may be anything
         }
         void* d = nullptr;
-        DRB_CUDA(cudaMalloc(&d, img.rgba.size()));
+        DRB_CUDA(cudaMallocAsync(&d, img.rgba.size(), s->stream));
         s->texture_storage.push_back(d);
-        DRB_CUDA(cudaMemcpy(d, img.rgba.data(), img.rgba.size(), cudaMemcpyHostToDevice));
+        DRB_CUDA(cudaMemcpyAsync(d, img.rgba.data(), img.rgba.size(), cudaMemcpyHostToDevice, s->stream));
+        DRB_CUDA(cudaStreamSynchronize(s->stream));      // img goes out of scope
         table[(size_t)i] = DevTexture{ (const uchar4*)d, img.w, img.h };
     }
-    if (int rc = dev_alloc(&s->textures, table.size())) return rc;
-    DRB_CUDA(cudaMemcpy(s->textures, table.data(), table.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
+    if (int rc = dev_alloc(&s->textures, table.size(), s->stream)) return rc;
+    DRB_CUDA(cudaMemcpyAsync(s->textures, table.data(), table.size() * sizeof(DevTexture), cudaMemcpyHostToDevice, s->stream));
+    DRB_CUDA(cudaStreamSynchronize(s->stream));
     drb_clear_error();
     return DRB_OK;
 }
 
 } // namespace
+
+void drb_host_scene_unpin(drb_host_scene* hs)
+{
+    if (hs && hs->pinned) { cudaHostUnregister((void*)hs->objects.data()); cudaGetLastError(); hs->pinned = false; }
+}
 
 extern "C" {
 
@@ -463,15 +646,19 @@ void drb_scene_free(drb_scene* s)
     if (!s) return;
     cudaSetDevice(s->device);
     drb_render_buffers_free(s);
-    cudaFree(s->nodes); cudaFree(s->prims); cudaFree(s->recs); cudaFree(s->orig_id); cudaFree(s->textures);
-    for (void* p : s->texture_storage) cudaFree(p);
-    cudaFree(s->dbg.keys); cudaFree(s->dbg.order); cudaFree(s->dbg.parent); cudaFree(s->dbg.left); cudaFree(s->dbg.right);
-    cudaFree(s->dbg.node_min); cudaFree(s->dbg.node_max);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaStream_t st = s->stream;
+    for (void* p : { (void*)s->nodes, (void*)s->prims, (void*)s->recs, (void*)s->orig_id, (void*)s->textures, (void*)s->dbg.keys,
+                     (void*)s->dbg.order, (void*)s->dbg.parent, (void*)s->dbg.left, (void*)s->dbg.right, (void*)s->dbg.node_min,
+                     (void*)s->dbg.node_max, (void*)s->tree.left, (void*)s->tree.right, (void*)s->tree.node_min, (void*)s->tree.node_max })
+        if (p) cudaFreeAsync(p, st);
+    for (void* p : s->texture_storage) cudaFreeAsync(p, st);
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     delete s;
 }
 
-int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out)
+int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out) { return drb_scene_create_ex(hs, device, 0u, out); }
+
+int drb_scene_create_ex(const drb_host_scene* hs, int device, uint32_t build_flags, drb_scene** out)
 {
     if (!hs || !out) { drb_set_error("drb_scene_create: null argument"); return DRB_ERR_ARG; }
     *out = nullptr;
@@ -485,9 +672,16 @@ int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out)
     DRB_CUDA(cudaSetDevice(device));
     auto s = new drb_scene();
     s->device = device;
+    s->build_flags = build_flags;
     s->settings = hs->settings;
     cudaError_t ce = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { drb_set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); delete s; return DRB_ERR_CUDA; }
+    if (int prc = retain_pool(device)) { cudaStreamDestroy(s->stream); delete s; return prc; }
+    // page-lock the object lines once per host scene so the upload runs at PCIe speed (and again for free next frame)
+    if (!hs->objects.empty() && !hs->pinned) {
+        if (cudaHostRegister((void*)hs->objects.data(), hs->objects.size() * sizeof(drb_object), cudaHostRegisterDefault) == cudaSuccess) hs->pinned = true;
+        else cudaGetLastError();
+    }
     int rc = upload_textures(s, hs);
     if (rc == DRB_OK) rc = build_tree(s, hs);
     if (rc != DRB_OK) { std::string keep = drb_last_error(); drb_scene_free(s); drb_set_error("%s", keep.c_str()); return rc; }
@@ -541,6 +735,27 @@ int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* 
         }
         if (node_max) {
             DRB_CUDA(cudaMemcpy(tmp.data(), s->dbg.node_max, ni * 16, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < ni; ++i) { node_max[3*i] = tmp[i].x; node_max[3*i+1] = tmp[i].y; node_max[3*i+2] = tmp[i].z; }
+        }
+    }
+    return DRB_OK;
+}
+
+int drb_scene_tree(const drb_scene* s, int32_t* left, int32_t* right, float* node_min, float* node_max)
+{
+    if (!s) { drb_set_error("drb_scene_tree: null scene"); return DRB_ERR_ARG; }
+    DRB_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->nprims, ni = n > 1 ? n - 1 : 0;
+    if (left && ni) DRB_CUDA(cudaMemcpy(left, s->tree.left, ni * 4, cudaMemcpyDeviceToHost));
+    if (right && ni) DRB_CUDA(cudaMemcpy(right, s->tree.right, ni * 4, cudaMemcpyDeviceToHost));
+    if ((node_min || node_max) && ni) {
+        std::vector<float4> tmp(ni);
+        if (node_min) {
+            DRB_CUDA(cudaMemcpy(tmp.data(), s->tree.node_min, ni * 16, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < ni; ++i) { node_min[3*i] = tmp[i].x; node_min[3*i+1] = tmp[i].y; node_min[3*i+2] = tmp[i].z; }
+        }
+        if (node_max) {
+            DRB_CUDA(cudaMemcpy(tmp.data(), s->tree.node_max, ni * 16, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < ni; ++i) { node_max[3*i] = tmp[i].x; node_max[3*i+1] = tmp[i].y; node_max[3*i+2] = tmp[i].z; }
         }
     }

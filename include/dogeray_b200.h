@@ -111,6 +111,11 @@ void drb_settings_default(drb_settings* out);
 typedef struct drb_scene drb_scene;
 
 int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out);
+/* Same with build flags.  DRB_BUILD_LBVH_ONLY keeps the Karras hierarchy as the traversal tree (fastest
+ * build); by default the hierarchy is rebuilt over the same Morton order by SAH-guided agglomerative
+ * clustering, which traverses ~1.4x faster. */
+#define DRB_BUILD_LBVH_ONLY 1u
+int drb_scene_create_ex(const drb_host_scene* hs, int device, uint32_t build_flags, drb_scene** out);
 /* convenience: drb_host_scene_load + drb_scene_create */
 int drb_scene_load(const char* rts_path, const char* tex_dir, int device, drb_scene** out);
 void drb_scene_free(drb_scene* s);
@@ -122,7 +127,8 @@ typedef struct drb_build_info {
     int64_t nprims, nnodes;
     float bounds_min[3], bounds_max[3];
     float upload_ms, build_ms;
-    int32_t max_depth;
+    int32_t max_depth;          /* height of the traversal tree */
+    int32_t rebuild_iterations; /* clustering rounds of the SAH-guided rebuild (0 with DRB_BUILD_LBVH_ONLY) */
 } drb_build_info;
 int drb_scene_build_info(const drb_scene* s, drb_build_info* out);
 
@@ -133,6 +139,10 @@ int drb_scene_build_info(const drb_scene* s, drb_build_info* out);
  * internal node. */
 int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* parent, int32_t* left, int32_t* right,
                    float* node_min, float* node_max);
+
+/* The hierarchy the traversal nodes were emitted from, root = node 0, same child encoding as
+ * drb_scene_lbvh; equals the Karras tree with DRB_BUILD_LBVH_ONLY.  For the bit-exact host check. */
+int drb_scene_tree(const drb_scene* s, int32_t* left, int32_t* right, float* node_min, float* node_max);
 
 /* ---- rendering ------------------------------------------------------------------------ */
 typedef struct drb_opts {

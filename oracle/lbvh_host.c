@@ -133,3 +133,73 @@ int lbvh_host_build(const float* bmin, const float* bmax, int n, uint64_t* keys,
     free(visits); free(height); free(lmin); free(lmax); free(leaf_parent);
     return tree_height;
 }
+
+/* ---- host mirror of the SAH-guided rebuild (k_ploc_* in dogeray_b200/csrc/scene.cu) ----------------
+ * lmin/lmax: n*3 leaf boxes in SORTED order.  Outputs in the final labelling (root = node 0): left/right
+ * [n-1] with leaves as ~sorted_position, node_min/node_max [(n-1)*3].  Returns the tree height. */
+static float union_half_area(const float* alo, const float* ahi, const float* blo, const float* bhi)
+{
+    float ex = fmaxf(ahi[0], bhi[0]) - fminf(alo[0], blo[0]);
+    float ey = fmaxf(ahi[1], bhi[1]) - fminf(alo[1], blo[1]);
+    float ez = fmaxf(ahi[2], bhi[2]) - fminf(alo[2], blo[2]);
+    return ex * ey + ey * ez + ez * ex;
+}
+
+int ploc_host_build(const float* lmin, const float* lmax, int n, int radius, int32_t* left, int32_t* right, float* node_min, float* node_max)
+{
+    if (n <= 1) return n;
+    size_t N = (size_t)n;
+    int32_t* cid[2]; float* cmn[2]; float* cmx[2]; int* chg[2];
+    for (int k = 0; k < 2; k++) { cid[k] = malloc(4 * N); cmn[k] = malloc(12 * N); cmx[k] = malloc(12 * N); chg[k] = malloc(4 * N); }
+    int32_t* nn = malloc(4 * N);
+    int32_t* pl = malloc(4 * N); int32_t* pr = malloc(4 * N); float* pmin = malloc(12 * N); float* pmax = malloc(12 * N);
+    for (int i = 0; i < n; i++) { cid[0][i] = ~i; chg[0][i] = 0; }
+    memcpy(cmn[0], lmin, 12 * N); memcpy(cmx[0], lmax, 12 * N);
+    int cur = 0, m = n, node_base = 0, height = 0;
+    while (m > 1) {
+        for (int i = 0; i < m; i++) {
+            float best = 3.4e38f; int bj = -1;
+            int j0 = i - radius < 0 ? 0 : i - radius, j1 = i + radius > m - 1 ? m - 1 : i + radius;
+            for (int j = j0; j <= j1; j++) {
+                if (j == i) continue;
+                float a = union_half_area(cmn[cur] + 3 * i, cmx[cur] + 3 * i, cmn[cur] + 3 * j, cmx[cur] + 3 * j);
+                if (a < best) { best = a; bj = j; }
+            }
+            if (bj < 0) bj = (i ^ 1) < m ? (i ^ 1) : i - 1;
+            nn[i] = bj;
+        }
+        int pos = 0, merges = 0, nx = cur ^ 1;
+        for (int i = 0; i < m; i++) {
+            int j = nn[i];
+            int mutual = j >= 0 && j < m && nn[j] == i;
+            if (mutual && i > j) continue;
+            if (mutual && i < j) {
+                int node = node_base + merges++;
+                pl[node] = cid[cur][i]; pr[node] = cid[cur][j];
+                for (int a = 0; a < 3; a++) {
+                    pmin[3 * node + a] = fminf(cmn[cur][3 * i + a], cmn[cur][3 * j + a]);
+                    pmax[3 * node + a] = fmaxf(cmx[cur][3 * i + a], cmx[cur][3 * j + a]);
+                }
+                int h = (chg[cur][i] > chg[cur][j] ? chg[cur][i] : chg[cur][j]) + 1;
+                cid[nx][pos] = node; chg[nx][pos] = h; height = h;
+                memcpy(cmn[nx] + 3 * pos, pmin + 3 * node, 12); memcpy(cmx[nx] + 3 * pos, pmax + 3 * node, 12);
+            } else {
+                cid[nx][pos] = cid[cur][i]; chg[nx][pos] = chg[cur][i];
+                memcpy(cmn[nx] + 3 * pos, cmn[cur] + 3 * i, 12); memcpy(cmx[nx] + 3 * pos, cmx[cur] + 3 * i, 12);
+            }
+            pos++;
+        }
+        if (merges == 0) break;
+        node_base += merges; m = pos; cur = nx;
+    }
+    height = chg[cur][0];
+    for (int i = 0; i < n - 1; i++) {
+        int dst = (n - 2) - i;
+        left[dst] = pl[i] < 0 ? pl[i] : (n - 2) - pl[i];
+        right[dst] = pr[i] < 0 ? pr[i] : (n - 2) - pr[i];
+        memcpy(node_min + 3 * dst, pmin + 3 * i, 12); memcpy(node_max + 3 * dst, pmax + 3 * i, 12);
+    }
+    for (int k = 0; k < 2; k++) { free(cid[k]); free(cmn[k]); free(cmx[k]); free(chg[k]); }
+    free(nn); free(pl); free(pr); free(pmin); free(pmax);
+    return height;
+}

@@ -235,8 +235,19 @@ def test_gpu_lbvh_bit_exact_against_host_build():
             assert np.array_equal(dev[k], host[k]), k
         assert np.array_equal(dev["node_min"], host["node_min"]) and np.array_equal(dev["node_max"], host["node_max"])
         bi = sc.build_info
-        assert bi.max_depth == host["height"]
         assert np.array_equal(np.array(list(bi.bounds_min) + list(bi.bounds_max), np.float32), host["scene_bounds"])
+        # the SAH-guided rebuild over the same sorted leaves, against its host mirror
+        if len(objs) > 1:
+            lmin, lmax = bmin[host["order"]], bmax[host["order"]]
+            ph = restated.ploc_host(lmin, lmax)
+            dt = sc.tree()
+            assert np.array_equal(dt["left"], ph["left"]) and np.array_equal(dt["right"], ph["right"])
+            assert np.array_equal(dt["node_min"], ph["node_min"]) and np.array_equal(dt["node_max"], ph["node_max"])
+            assert bi.max_depth == ph["height"] and bi.rebuild_iterations > 0
+            lb = drb.Scene.from_host(drb.HostScene.from_objects(objs), build_flags=drb.BUILD_LBVH_ONLY)
+            assert lb.build_info.max_depth == host["height"] and lb.build_info.rebuild_iterations == 0
+            lt = lb.tree()
+            assert np.array_equal(lt["left"], host["left"]) and np.array_equal(lt["right"], host["right"])
 
 
 def test_tonemap_device_matches_host():

@@ -118,3 +118,18 @@ def test_host_lbvh_is_a_valid_tree():
                 assert (t["node_min"][k] <= lo).all() and (t["node_max"][k] >= hi).all()
         assert (seen_leaf == 1).all() and (seen_node == 1).all() and t["parent"][0] == -1
         assert np.array_equal(t["node_min"][0], (c - e).min(0)) and np.array_equal(t["node_max"][0], (c + e).max(0))
+        # the SAH-guided rebuild over the same sorted leaves is a valid tree too, with root 0 and parents first
+        lmin, lmax = (c - e)[t["order"]], (c + e)[t["order"]]
+        p = restated.ploc_host(lmin, lmax)
+        seen = np.zeros(n, int)
+        stack = [0]
+        while stack:
+            k = stack.pop()
+            for ch in (p["left"][k], p["right"][k]):
+                if ch < 0:
+                    seen[~ch] += 1
+                    assert (p["node_min"][k] <= lmin[~ch]).all() and (p["node_max"][k] >= lmax[~ch]).all()
+                else:
+                    assert ch > k
+                    stack.append(int(ch))
+        assert (seen == 1).all() and np.array_equal(p["node_min"][0], (c - e).min(0))
