@@ -13,20 +13,33 @@
 //   c1xy = (c1.min.x, c1.max.x, c1.min.y, c1.max.y)
 //   cz   = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
 //   link = (child0, child1, 0, 0); child >= 0: node index, child < 0: leaf, ~child = primitive slot
-struct __align__(16) BvhNode {
+struct __align__(32) BvhNode {
     float4 c0xy, c1xy, cz;
     int4 link;
 };
+
+#ifdef __CUDACC__
+// one 256-bit read-only global load (PTX ISA 8.8, sm_100+): half the L1 data-pipe wavefronts of two LDG.128
+struct __align__(32) f8 { float4 lo, hi; };
+__device__ __forceinline__ f8 ldg256(const void* p)
+{
+    f8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+#endif
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
-// 48 B primitive, in tree (Morton) order.
-//   triangle: a = (v0, kind 0), b = (v1 - v0, 0), c = (v2 - v0, 0)   (edges precomputed in float,
+// 64 B primitive, in tree (Morton) order, fetched with two 256-bit loads (LDG.E.256 on sm_100).
+//   triangle: a = (v0, kind 0), b = (v1 - v0, 0), c = (v2 - v0, 0), d = spare   (edges precomputed in float,
 //             exactly the subtraction hit_tri does first, kernel.cu:287-288)
 //   sphere:   a = (centre, kind 1), b = (radius, 0, 0, 0)
-struct __align__(16) Prim {
-    float4 a, b, c;
+struct __align__(32) Prim {
+    float4 a, b, c, d;
 };
-static_assert(sizeof(Prim) == 48, "Prim must be 48 bytes");
+static_assert(sizeof(Prim) == 64, "Prim must be 64 bytes");
 #define DRB_KIND_TRI 0
 #define DRB_KIND_SPHERE 1
 

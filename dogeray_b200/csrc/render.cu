@@ -24,14 +24,18 @@
 #include "philox.cuh"
 #include "vec.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 namespace {
 
-constexpr int kStackSize = 96;          // >= kMaxTreeHeight in scene.cu
+constexpr int kStackSize = 100;         // > kMaxTreeHeight in scene.cu (+ the sentinel)
+constexpr int kSmemStack = 32;          // levels of the traversal stack kept in shared memory
 constexpr uint32_t kInvalidPid = 0xFFFFFFFFu;
 constexpr float kTMax = 10000.0f;       // singlehit's mindist / aabb2's t_max, kernel.cu:246, 435
 constexpr float kEps = 0.0001f;         // hit_tri's EPSILON, kernel.cu:283
@@ -156,10 +160,10 @@ DRB_D float safe_inv(float d)
 // of singlehit / hit (kernel.cu:449, 488): EPS < t < 10000 and t < best
 DRB_D void intersect_prim(const Prim* __restrict__ prims, int slot, const f3& o, const f3& d, float& best, int& bestp)
 {
-    const float4 pa = __ldg(&prims[slot].a);
-    const float4 pb = __ldg(&prims[slot].b);
+    const f8 pab = ldg256(&prims[slot].a);
+    const float4 pa = pab.lo, pb = pab.hi;
     if (__float_as_int(pa.w) == DRB_KIND_TRI) {
-        const float4 pc = __ldg(&prims[slot].c);
+        const float4 pc = ldg256(&prims[slot].c).lo;
         const f3 v0 = xyz(pa), e1 = xyz(pb), e2 = xyz(pc);
         const f3 h = cross(d, e2);
         const float a = dot(e1, h);
@@ -188,25 +192,84 @@ DRB_D void intersect_prim(const Prim* __restrict__ prims, int slot, const f3& o,
     }
 }
 
-DRB_D void trace_closest(const DevScene& sc, float scene_scale, const f3& o, const f3& d, float& best, int& bestp)
+constexpr int kSentinel = (int)0x80000000;     // bottom of every traversal stack: "this lane has no ray in flight"
+
+// Persistent traversal with per-lane dynamic ray fetch (after Aila & Laine, "Understanding the Efficiency of
+// Ray Traversal on GPUs", HPG 2009).  The reference walks its threaded tree one thread per pixel (hit(),
+// kernel.cu:468-512); incoherent bounces then leave most lanes of a warp idle while the longest ray
+// finishes.  Here a lane keeps (ray, node, stack) state.  Every iteration each lane does ONE step -- an
+// internal node (both child boxes of the 64 B node, near child next, far child pushed) or the leaf it
+// popped (one primitive) -- and the warp re-converges.  When fewer than `refill` lanes still have a ray,
+// the idle lanes claim fresh rays from the queue with ONE atomic per warp (ballot + popc + shfl), so warps
+// stay populated until the queue runs dry.  (A while-while variant measured slower on B200: with
+// one-primitive leaves, lanes that reach a leaf wait for the slowest descent.)
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Queues q, int cur, int refill, int leaf_batch, int step_min,
+                                               const uint32_t* __restrict__ order)
 {
-    best = kTMax; bestp = -1;
-    if (sc.nprims == 0) return;
-    const float ix = safe_inv(d.x), iy = safe_inv(d.y), iz = safe_inv(d.z);
-    // per-ray slab padding: boxes are stored tight; the ray sees them grown by a few ulps of the
-    // distances involved, so a hit the triangle test accepts by rounding is never culled by a box
-    const float pad = (fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + scene_scale) * 1.9073486e-6f;
-    const float oxl = (o.x + pad) * ix, oxh = (o.x - pad) * ix;
-    const float oyl = (o.y + pad) * iy, oyh = (o.y - pad) * iy;
-    const float ozl = (o.z + pad) * iz, ozh = (o.z - pad) * iz;
-    int stack[kStackSize];
+    const uint32_t count = q.counters[cur];
+    const float4* __restrict__ ro = q.ray_o[cur];
+    const float4* __restrict__ rdv = q.ray_d[cur];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    int node = kSentinel;
+    int leaf = 0;                                   // stashed leaf (~primitive slot, always < 0), 0 = none
+    uint32_t ray = 0xFFFFFFFFu;
+    bool exhausted = false;                         // warp-uniform: the queue has been handed out completely
+    f3 o = mk3(0.f), d = mk3(0.f);
+    float ix = 0.f, iy = 0.f, iz = 0.f, oxl = 0.f, oxh = 0.f, oyl = 0.f, oyh = 0.f, ozl = 0.f, ozh = 0.f;
+    float best = kTMax; int bestp = -1;
+    // short stack in shared memory, [level][thread]: every lane owns a bank, so pushes and pops at different
+    // depths are still one conflict-free wavefront per warp (a local-memory stack costs one L1 wavefront per
+    // distinct depth).  Levels beyond kSmemStack spill to local memory (trees taller than 32 are rare).
+    __shared__ int s_stack[kSmemStack][128];
+    int spill[kStackSize - kSmemStack];
     int sp = 0;
-    int node = 0;
+    const unsigned tid = threadIdx.x;
+#define DRB_PUSH(v) do { const int v__ = (v); if (sp < kSmemStack) s_stack[sp][tid] = v__; else spill[sp - kSmemStack] = v__; ++sp; } while (0)
+#define DRB_POP() (--sp, sp < kSmemStack ? s_stack[sp][tid] : spill[sp - kSmemStack])
+
     for (;;) {
+        // ---- refill idle lanes ----------------------------------------------------------------------
+        const bool idle = (node == kSentinel && leaf == 0);
+        const unsigned midle = __ballot_sync(0xffffffffu, idle);
+        if (midle == 0xffffffffu && exhausted) break;
+        if (!exhausted && (midle == 0xffffffffu || 32 - __popc(midle) < refill)) {
+            const int leader = __ffs(midle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&q.counters[CNT_TICKET], (uint32_t)__popc(midle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (uint32_t)__popc(midle) >= count) exhausted = true;
+            if (idle) {
+                const uint32_t k = base + (uint32_t)__popc(midle & lt_mask);
+                if (k < count) {
+                    const uint32_t i = order ? order[k] : k;        // queue position of the k-th ray in traversal order
+                    const float4 o4 = ro[i], d4 = rdv[i];
+                    if (__float_as_uint(o4.w) == kInvalidPid || sc.nprims == 0) {
+                        q.hit[i] = make_uint2(__float_as_uint(-1.0f), 0xFFFFFFFFu);
+                    } else {
+                        ray = i;
+                        o = xyz(o4); d = xyz(d4);
+                        ix = safe_inv(d.x); iy = safe_inv(d.y); iz = safe_inv(d.z);
+                        // per-ray slab padding: boxes are stored tight; the ray sees them grown by a few ulps of the
+                        // distances involved, so a hit the triangle test accepts by rounding is never culled by a box
+                        const float pad = (fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + scene_scale) * 1.9073486e-6f;
+                        oxl = (o.x + pad) * ix; oxh = (o.x - pad) * ix;
+                        oyl = (o.y + pad) * iy; oyh = (o.y - pad) * iy;
+                        ozl = (o.z + pad) * iz; ozh = (o.z - pad) * iz;
+                        best = kTMax; bestp = -1;
+                        sp = 0; DRB_PUSH(kSentinel);
+                        node = 0;
+                    }
+                }
+            }
+        }
+        // ---- one traversal step per lane --------------------------------------------------------------
         if (node >= 0) {
             const BvhNode* np = sc.nodes + node;
-            const float4 n0 = __ldg(&np->c0xy), n1 = __ldg(&np->c1xy), nz = __ldg(&np->cz);
-            const int4 link = __ldg(&np->link);
+            const f8 nA = ldg256(&np->c0xy), nB = ldg256(&np->cz);
+            const float4 n0 = nA.lo, n1 = nA.hi, nz = nB.lo;
+            const int2 link = make_int2(__float_as_int(nB.hi.x), __float_as_int(nB.hi.y));
             float a, b;
             a = fmaf(n0.x, ix, -oxl); b = fmaf(n0.y, ix, -oxh);
             float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
@@ -224,44 +287,31 @@ DRB_D void trace_closest(const DevScene& sc, float scene_scale, const f3& o, con
             const bool h1 = fmaxf(tn1, 0.0f) <= fminf(tf1, best);
             if (h0 && h1) {
                 const bool swap = tn1 < tn0;
-                stack[sp++] = swap ? link.x : link.y;
+                DRB_PUSH(swap ? link.x : link.y);
                 node = swap ? link.y : link.x;
-                continue;
-            }
-            if (h0) { node = link.x; continue; }
-            if (h1) { node = link.y; continue; }
-        } else {
-            intersect_prim(sc.prims, ~node, o, d, best, bestp);
+            } else if (h0) node = link.x;
+            else if (h1) node = link.y;
+            else node = DRB_POP();
         }
-        if (sp == 0) break;
-        node = stack[--sp];
-    }
-}
-
-// persistent warps: each warp claims 32 consecutive rays per ticket
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Queues q, int cur)
-{
-    const uint32_t count = q.counters[cur];
-    const float4* __restrict__ ro = q.ray_o[cur];
-    const float4* __restrict__ rdv = q.ray_d[cur];
-    const unsigned lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&q.counters[CNT_TICKET], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        const uint32_t i = base + lane;
-        if (i < count) {
-            const float4 o4 = ro[i], d4 = rdv[i];
-            float t = -1.0f; int p = -1;
-            if (__float_as_uint(o4.w) != kInvalidPid) {
-                float best; int bestp;
-                trace_closest(sc, scene_scale, xyz(o4), xyz(d4), best, bestp);
-                if (bestp >= 0) { t = best; p = bestp; }
+        // ---- postponed leaves -------------------------------------------------------------------------
+        // A lane that arrives at a leaf stashes it and keeps descending; the (long, divergent) primitive test
+        // runs for the whole warp at once when enough lanes hold a leaf, or when too few lanes can still step.
+        if (node < 0 && node != kSentinel && leaf == 0) { leaf = node; node = DRB_POP(); }
+        const unsigned mpend = __ballot_sync(0xffffffffu, leaf != 0);
+        if (mpend) {
+            const unsigned mstep = __ballot_sync(0xffffffffu, node >= 0);
+            if (__popc(mpend) >= leaf_batch || __popc(mstep) < step_min) {
+                if (leaf != 0) { intersect_prim(sc.prims, ~leaf, o, d, best, bestp); leaf = 0; }
             }
-            q.hit[i] = make_uint2(__float_as_uint(t), (uint32_t)p);
+        }
+        // ---- retire -----------------------------------------------------------------------------------
+        if (node == kSentinel && leaf == 0 && ray != 0xFFFFFFFFu) {
+            q.hit[ray] = bestp >= 0 ? make_uint2(__float_as_uint(best), (uint32_t)bestp) : make_uint2(__float_as_uint(-1.0f), 0xFFFFFFFFu);
+            ray = 0xFFFFFFFFu;
         }
     }
+#undef DRB_PUSH
+#undef DRB_POP
 }
 
 // ---- shading ---------------------------------------------------------------------------------------
@@ -325,7 +375,7 @@ DRB_D f3 environment(const DevScene& sc, const FrameParams& fp, f3 raydir)
     return mk3(omt) * mk3(1.0f) + mk3(t) * mk3(0.5f, 0.7f, 1.0f);
 }
 
-__global__ void __launch_bounds__(256) k_shade(DevScene sc, FrameParams fp, Queues q, int cur, int last_bounce)
+__global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Queues q, int cur, int last_bounce)
 {
     const uint32_t count = q.counters[cur];
     const int nxt = cur ^ 1;
@@ -483,6 +533,33 @@ __global__ void __launch_bounds__(256) k_shade(DevScene sc, FrameParams fp, Queu
     if (lane == 0 && local_rays) atomicAdd(reinterpret_cast<unsigned long long*>(&q.counters[CNT_RAYS]), (unsigned long long)local_rays);
 }
 
+// Sort key of a queued ray: direction octant (3 bits) above the 21-bit Morton code of the origin's cell in a
+// 128^3 grid over the scene bounds.  Rays that start close together and head the same way end up in the
+// same warp: they touch the same nodes (fewer distinct lines per load = fewer L1 wavefronts) and leave the
+// tree at similar times (fewer idle lanes).  Purely a scheduling order: results do not depend on it.
+__global__ void __launch_bounds__(256) k_ray_keys(const float4* __restrict__ ro, const float4* __restrict__ rdv, uint32_t count,
+                                                   float3 lo, float3 inv_ext, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float4 o = ro[i], d = rdv[i];
+    auto cell = [](float v, float l, float s) -> uint32_t {
+        const float x = fminf(fmaxf((v - l) * s * 128.0f, 0.0f), 127.0f);
+        return (uint32_t)x;
+    };
+    auto spread7 = [](uint32_t v) -> uint32_t {                 // 7 bits -> every third bit
+        v = (v | (v << 16)) & 0x030000FFu;
+        v = (v | (v << 8)) & 0x0300F00Fu;
+        v = (v | (v << 4)) & 0x030C30C3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    };
+    const uint32_t m = (spread7(cell(o.x, lo.x, inv_ext.x)) << 2) | (spread7(cell(o.y, lo.y, inv_ext.y)) << 1) | spread7(cell(o.z, lo.z, inv_ext.z));
+    const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    keys[i] = (oct << 21) | m;
+    vals[i] = i;
+}
+
 // counters for the next bounce: clear the queue that k_shade is about to fill and the trace ticket
 __global__ void k_prepare(uint32_t* counters, int clear_queue, int set_queue, uint32_t set_value)
 {
@@ -571,6 +648,11 @@ struct RenderBuffers {
     size_t capacity = 0;                // path slots
     Queues q{};
     int trace_blocks = 0, shade_blocks = 0;
+    // ray reordering (one sort per bounce): keys / ray indices, double-buffered, + CUB scratch
+    uint32_t* sort_keys[2] = { nullptr, nullptr };
+    uint32_t* sort_vals[2] = { nullptr, nullptr };
+    void* sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
 };
 
 namespace {
@@ -631,6 +713,13 @@ int ensure_buffers(drb_scene* s, size_t slots)
     DRB_CUDA(cudaMallocAsync((void**)&q.hit, slots * sizeof(uint2), st));
     DRB_CUDA(cudaMallocAsync((void**)&q.contrib, slots * sizeof(float4), st));
     DRB_CUDA(cudaMallocAsync((void**)&q.counters, CNT_WORDS * sizeof(uint32_t), st));
+    for (int k = 0; k < 2; ++k) {
+        DRB_CUDA(cudaMallocAsync((void**)&rb->sort_keys[k], slots * sizeof(uint32_t), st));
+        DRB_CUDA(cudaMallocAsync((void**)&rb->sort_vals[k], slots * sizeof(uint32_t), st));
+    }
+    DRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, rb->sort_tmp_bytes, rb->sort_keys[0], rb->sort_keys[1], rb->sort_vals[0], rb->sort_vals[1],
+                                             (int)std::min<size_t>(slots, 0x7FFFFFFF), 0, 24, st));
+    DRB_CUDA(cudaMallocAsync(&rb->sort_tmp, rb->sort_tmp_bytes ? rb->sort_tmp_bytes : 16, st));
     DRB_CUDA(cudaMemsetAsync(q.counters, 0, CNT_WORDS * sizeof(uint32_t), st));
     DRB_CUDA(cudaStreamSynchronize(st));             // the buffers may be used from a caller-provided stream next
     rb->capacity = slots;
@@ -638,7 +727,7 @@ int ensure_buffers(drb_scene* s, size_t slots)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
     DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, 128, 0));
     rb->trace_blocks = sms * std::max(per_sm, 1);
-    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 256, 0));
+    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 128, 0));
     rb->shade_blocks = sms * std::max(per_sm, 1);
     return DRB_OK;
 }
@@ -665,6 +754,17 @@ int check_settings(const drb_settings* st)
     if (st->max_depth < 0) { drb_set_error("bad max_depth %d", st->max_depth); return DRB_ERR_ARG; }
     return DRB_OK;
 }
+
+// lanes-still-traversing threshold below which a warp refills its idle lanes (tunable for experiments)
+int g_refill = []() { const char* e = getenv("DOGERAY_B200_REFILL"); int v = e ? atoi(e) : 20; return v < 0 ? 0 : (v > 33 ? 33 : v); }();
+
+// stashed leaves are intersected when at least g_leaf_batch lanes hold one, or fewer than g_step_min lanes can descend
+int g_leaf_batch = []() { const char* e = getenv("DOGERAY_B200_LEAF_BATCH"); int v = e ? atoi(e) : 12; return v < 1 ? 1 : v; }();
+int g_step_min = []() { const char* e = getenv("DOGERAY_B200_STEP_MIN"); int v = e ? atoi(e) : 20; return v < 1 ? 1 : v; }();
+
+// reorder a bounce's rays before tracing when the queue holds at least this many (0 = never, the default:
+// on B200 the sort costs more than the ~5 % of traversal time it saves on the 1 M-triangle workload)
+long g_sort_min = []() { const char* e = getenv("DOGERAY_B200_SORT_MIN"); return e ? atol(e) : 0L; }();
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;
@@ -719,11 +819,30 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
         k_prepare<<<1, 32, 0, stream>>>(q.counters, 1, 0, nslots);
         launches += 2;
         int cur = 0;
+        uint32_t live = nslots;
         for (int b = 0; b < st->max_depth; ++b) {
+            const uint32_t* order = nullptr;
+            if (b > 0) {
+                // the queue size decides whether the bounce is worth reordering, and ends the batch early
+                DRB_CUDA(cudaMemcpyAsync(&live, q.counters + cur, sizeof live, cudaMemcpyDeviceToHost, stream));
+                DRB_CUDA(cudaStreamSynchronize(stream));
+                if (live == 0) break;
+                if (g_sort_min > 0 && (long)live >= g_sort_min) {
+                    const float3 lo = make_float3(s->info.bounds_min[0], s->info.bounds_min[1], s->info.bounds_min[2]);
+                    auto inv = [&](int a) { const float e = s->info.bounds_max[a] - s->info.bounds_min[a]; return e > 0.f ? 1.0f / e : 0.f; };
+                    k_ray_keys<<<(live + 255) / 256, 256, 0, stream>>>(q.ray_o[cur], q.ray_d[cur], live, lo, make_float3(inv(0), inv(1), inv(2)),
+                                                                       rb->sort_keys[0], rb->sort_vals[0]);
+                    size_t tb = rb->sort_tmp_bytes;
+                    DRB_CUDA(cub::DeviceRadixSort::SortPairs(rb->sort_tmp, tb, rb->sort_keys[0], rb->sort_keys[1], rb->sort_vals[0], rb->sort_vals[1],
+                                                             (int)live, 0, 24, stream));
+                    order = rb->sort_vals[1];
+                    launches += 4;
+                }
+            }
             if (stats) { auto e0 = pool.get(), e1 = pool.get(); trace_ev.push_back({ e0, e1 }); DRB_CUDA(cudaEventRecord(e0, stream)); }
-            k_trace<<<rb->trace_blocks, 128, 0, stream>>>(sc, fp.scene_scale, q, cur);
+            k_trace<<<rb->trace_blocks, 128, 0, stream>>>(sc, fp.scene_scale, q, cur, g_refill, g_leaf_batch, g_step_min, order);
             if (stats) DRB_CUDA(cudaEventRecord(trace_ev.back().second, stream));
-            k_shade<<<rb->shade_blocks, 256, 0, stream>>>(sc, fp, q, cur, b == st->max_depth - 1 ? 1 : 0);
+            k_shade<<<std::min<uint32_t>((uint32_t)rb->shade_blocks, (live + 127u) / 128u), 128, 0, stream>>>(sc, fp, q, cur, b == st->max_depth - 1 ? 1 : 0);
             k_prepare<<<1, 32, 0, stream>>>(q.counters, cur, -1, 0u);
             launches += 3; trace_launches += 1;
             cur ^= 1;
@@ -762,6 +881,8 @@ void drb_render_buffers_free(drb_scene* s)
     cudaDeviceSynchronize();                          // renders may have run on caller streams
     for (int k = 0; k < 2; ++k) { cudaFreeAsync(q.ray_o[k], st); cudaFreeAsync(q.ray_d[k], st); cudaFreeAsync(q.thr[k], st); }
     cudaFreeAsync(q.hit, st); cudaFreeAsync(q.contrib, st); cudaFreeAsync(q.counters, st);
+    for (int k = 0; k < 2; ++k) { cudaFreeAsync(s->rb->sort_keys[k], st); cudaFreeAsync(s->rb->sort_vals[k], st); }
+    cudaFreeAsync(s->rb->sort_tmp, st);
     delete s->rb;
     s->rb = nullptr;
 }
@@ -860,7 +981,7 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     const uint32_t nn = (uint32_t)n;
     k_load_rays<<<(nn + 255) / 256, 256, 0, stream>>>(d_o, d_d, nn, q);
     k_prepare<<<1, 32, 0, stream>>>(q.counters, -1, 0, nn);
-    k_trace<<<rb->trace_blocks, 128, 0, stream>>>(dev_scene(s), scene_scale(s), q, 0);
+    k_trace<<<rb->trace_blocks, 128, 0, stream>>>(dev_scene(s), scene_scale(s), q, 0, g_refill, g_leaf_batch, g_step_min, nullptr);
     k_store_ids<<<(nn + 255) / 256, 256, 0, stream>>>(q.hit, s->orig_id, nn, d_ids, d_t);
     cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
     if (t) cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);

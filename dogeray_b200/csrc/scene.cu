@@ -80,12 +80,14 @@ __global__ void k_pack(const drb_object* __restrict__ objs, int64_t n, const int
             p.a = make_float4(o.pos[0], o.pos[1], o.pos[2], __int_as_float(DRB_KIND_SPHERE));
             p.b = make_float4(o.dim[0], 0.f, 0.f, 0.f);
             p.c = make_float4(0.f, 0.f, 0.f, 0.f);
+            p.d = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int a = 0; a < 3; ++a) { lo[a] = o.pos[a] - r; hi[a] = o.pos[a] + r; }
             flags |= DRB_SF_SPHERE;
         } else {
             p.a = make_float4(o.pos[0], o.pos[1], o.pos[2], __int_as_float(DRB_KIND_TRI));
             p.b = make_float4(o.dim[0] - o.pos[0], o.dim[1] - o.pos[1], o.dim[2] - o.pos[2], 0.f);
             p.c = make_float4(o.rot[0] - o.pos[0], o.rot[1] - o.pos[1], o.rot[2] - o.pos[2], 0.f);
+            p.d = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int a = 0; a < 3; ++a) {
                 lo[a] = fminf(o.pos[a], fminf(o.dim[a], o.rot[a]));
                 hi[a] = fmaxf(o.pos[a], fmaxf(o.dim[a], o.rot[a]));
@@ -167,7 +169,7 @@ __global__ void k_gather(const int32_t* __restrict__ order, int n, const Prim* _
                          Prim* __restrict__ prims, ShadeRec* __restrict__ recs, int32_t* __restrict__ orig,
                          float4* __restrict__ lmin, float4* __restrict__ lmax)
 {
-    // 8 threads move one primitive: 3 + 8 float4 of payload
+    // 8 threads move one primitive: 4 + 8 float4 of payload
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int k = t >> 3, part = t & 7;
     if (k >= n) return;
@@ -175,15 +177,15 @@ __global__ void k_gather(const int32_t* __restrict__ order, int n, const Prim* _
     const float4* rs = reinterpret_cast<const float4*>(recs_u + src);
     float4* rd = reinterpret_cast<float4*>(recs + k);
     rd[part] = rs[part];
-    if (part < 3) {
+    if (part < 4) {
         const float4* ps = reinterpret_cast<const float4*>(prims_u + src);
         float4* pd = reinterpret_cast<float4*>(prims + k);
         pd[part] = ps[part];
-    } else if (part == 3) {
-        orig[k] = orig_u[src];
     } else if (part == 4) {
-        lmin[k] = bmin_u[src];
+        orig[k] = orig_u[src];
     } else if (part == 5) {
+        lmin[k] = bmin_u[src];
+    } else if (part == 6) {
         lmax[k] = bmax_u[src];
     }
 }
