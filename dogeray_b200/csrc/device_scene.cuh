@@ -8,15 +8,32 @@
 #include <string>
 #include <vector>
 
-// 64 B, 64 B-aligned binary node holding BOTH child boxes, so one visit decides both children.
-//   c0xy = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)
-//   c1xy = (c1.min.x, c1.max.x, c1.min.y, c1.max.y)
-//   cz   = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
-//   link = (child0, child1, 0, 0); child >= 0: node index, child < 0: leaf, ~child = primitive slot
+// 32 B binary node holding BOTH child boxes, fetched with ONE 256-bit load.
+// Child boxes are quantised to 16 bits per plane on a scene-wide grid (drb_quant_grid), rounded outwards
+// plus one quantum of margin, so a quantised box always contains the float box it came from:
+//   c0[a] = min_q | max_q << 16 for axis a of child 0, c1[a] likewise for child 1
+//   link[k] = child k: >= 0 node index, < 0 leaf, ~link = primitive slot
+// Traversal never converts the integers: PRMT drops a 16-bit half under the exponent 0x4B00 (the float
+// 2^23 + q) and one FMA with per-ray constants turns it into the plane's ray parameter.
 struct __align__(32) BvhNode {
-    float4 c0xy, c1xy, cz;
-    int4 link;
+    uint32_t c0[3], c1[3];
+    int32_t link[2];
 };
+static_assert(sizeof(BvhNode) == 32, "BvhNode must be 32 bytes");
+
+// The quantisation grid of one axis: 65528 quanta span the scene bounds, 4 spare quanta on each side so the
+// outward margin never clamps.  Same single float operations on host and device.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline void drb_quant_grid(float lo, float hi, float* qlo, float* qscale)
+{
+    float ext = hi - lo;
+    if (!(ext > 0.0f)) ext = 1.0f;
+    const float sc = ext / 65527.0f;
+    *qscale = sc;
+    *qlo = lo - 4.0f * sc;
+}
 
 #ifdef __CUDACC__
 // one 256-bit read-only global load (PTX ISA 8.8, sm_100+): half the L1 data-pipe wavefronts of two LDG.128
@@ -30,7 +47,6 @@ __device__ __forceinline__ f8 ldg256(const void* p)
     return r;
 }
 #endif
-static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
 // 64 B primitive, in tree (Morton) order, fetched with two 256-bit loads (LDG.E.256 on sm_100).
 //   triangle: a = (v0, kind 0), b = (v1 - v0, 0), c = (v2 - v0, 0), d = spare   (edges precomputed in float,

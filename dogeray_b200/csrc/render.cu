@@ -59,6 +59,7 @@ struct FrameParams {
 };
 
 struct DevScene {
+    float qlo[3], qscale[3];            // quantisation grid of the node boxes (drb_quant_grid)
     const BvhNode* nodes;
     const Prim* prims;
     const ShadeRec* recs;
@@ -217,7 +218,9 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Q
     uint32_t ray = 0xFFFFFFFFu;
     bool exhausted = false;                         // warp-uniform: the queue has been handed out completely
     f3 o = mk3(0.f), d = mk3(0.f);
-    float ix = 0.f, iy = 0.f, iz = 0.f, oxl = 0.f, oxh = 0.f, oyl = 0.f, oyh = 0.f, ozl = 0.f, ozh = 0.f;
+    // per-ray plane constants: t = fma(2^23 + q, s*, c*), near / far plane picked by the PRMT selectors
+    float sx = 0.f, sy = 0.f, sz = 0.f, cnx = 0.f, cny = 0.f, cnz = 0.f, cfx = 0.f, cfy = 0.f, cfz = 0.f;
+    uint32_t selx = 0x7410u, sely = 0x7410u, selz = 0x7410u;   // near-plane selector; far = near ^ 0x22
     float best = kTMax; int bestp = -1;
     // short stack in shared memory, [level][thread]: every lane owns a bank, so pushes and pops at different
     // depths are still one conflict-free wavefront per warp (a local-memory stack costs one L1 wavefront per
@@ -250,13 +253,19 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Q
                     } else {
                         ray = i;
                         o = xyz(o4); d = xyz(d4);
-                        ix = safe_inv(d.x); iy = safe_inv(d.y); iz = safe_inv(d.z);
-                        // per-ray slab padding: boxes are stored tight; the ray sees them grown by a few ulps of the
-                        // distances involved, so a hit the triangle test accepts by rounding is never culled by a box
+                        const float ix = safe_inv(d.x), iy = safe_inv(d.y), iz = safe_inv(d.z);
+                        // per-ray slab padding: on top of the quantisation margin the ray sees every box grown by a few
+                        // ulps of the distances involved, so a hit the triangle test accepts by rounding is never culled
                         const float pad = (fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + scene_scale) * 1.9073486e-6f;
-                        oxl = (o.x + pad) * ix; oxh = (o.x - pad) * ix;
-                        oyl = (o.y + pad) * iy; oyh = (o.y - pad) * iy;
-                        ozl = (o.z + pad) * iz; ozh = (o.z - pad) * iz;
+                        // plane coordinate = qlo + q * qscale; t = (coordinate -/+ pad - o) * inv, folded into one FMA on
+                        // the float 2^23 + q: t = (2^23 + q) * s + (c - 2^23 * s).  The near plane is the min plane for a
+                        // positive direction component and the max plane for a negative one.
+                        sx = sc.qscale[0] * ix; sy = sc.qscale[1] * iy; sz = sc.qscale[2] * iz;
+                        const float px = copysignf(pad, ix), py = copysignf(pad, iy), pz = copysignf(pad, iz);
+                        cnx = fmaf(-8388608.0f, sx, (sc.qlo[0] - o.x - px) * ix); cfx = fmaf(-8388608.0f, sx, (sc.qlo[0] - o.x + px) * ix);
+                        cny = fmaf(-8388608.0f, sy, (sc.qlo[1] - o.y - py) * iy); cfy = fmaf(-8388608.0f, sy, (sc.qlo[1] - o.y + py) * iy);
+                        cnz = fmaf(-8388608.0f, sz, (sc.qlo[2] - o.z - pz) * iz); cfz = fmaf(-8388608.0f, sz, (sc.qlo[2] - o.z + pz) * iz);
+                        selx = ix >= 0.f ? 0x7410u : 0x7432u; sely = iy >= 0.f ? 0x7410u : 0x7432u; selz = iz >= 0.f ? 0x7410u : 0x7432u;
                         best = kTMax; bestp = -1;
                         sp = 0; DRB_PUSH(kSentinel);
                         node = 0;
@@ -266,25 +275,20 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Q
         }
         // ---- one traversal step per lane --------------------------------------------------------------
         if (node >= 0) {
-            const BvhNode* np = sc.nodes + node;
-            const f8 nA = ldg256(&np->c0xy), nB = ldg256(&np->cz);
-            const float4 n0 = nA.lo, n1 = nA.hi, nz = nB.lo;
-            const int2 link = make_int2(__float_as_int(nB.hi.x), __float_as_int(nB.hi.y));
-            float a, b;
-            a = fmaf(n0.x, ix, -oxl); b = fmaf(n0.y, ix, -oxh);
-            float tn0 = fminf(a, b), tf0 = fmaxf(a, b);
-            a = fmaf(n0.z, iy, -oyl); b = fmaf(n0.w, iy, -oyh);
-            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-            a = fmaf(nz.x, iz, -ozl); b = fmaf(nz.y, iz, -ozh);
-            tn0 = fmaxf(tn0, fminf(a, b)); tf0 = fminf(tf0, fmaxf(a, b));
-            a = fmaf(n1.x, ix, -oxl); b = fmaf(n1.y, ix, -oxh);
-            float tn1 = fminf(a, b), tf1 = fmaxf(a, b);
-            a = fmaf(n1.z, iy, -oyl); b = fmaf(n1.w, iy, -oyh);
-            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-            a = fmaf(nz.z, iz, -ozl); b = fmaf(nz.w, iz, -ozh);
-            tn1 = fmaxf(tn1, fminf(a, b)); tf1 = fminf(tf1, fmaxf(a, b));
-            const bool h0 = fmaxf(tn0, 0.0f) <= fminf(tf0, best);
-            const bool h1 = fmaxf(tn1, 0.0f) <= fminf(tf1, best);
+            const f8 nd = ldg256(sc.nodes + node);                    // the whole node: one 256-bit load
+            const uint32_t w0 = __float_as_uint(nd.lo.x), w1 = __float_as_uint(nd.lo.y), w2 = __float_as_uint(nd.lo.z);
+            const uint32_t w3 = __float_as_uint(nd.lo.w), w4 = __float_as_uint(nd.hi.x), w5 = __float_as_uint(nd.hi.y);
+            const int2 link = make_int2(__float_as_int(nd.hi.z), __float_as_int(nd.hi.w));
+#define DRB_PLANE(w, sel, s_, c_) fmaf(__uint_as_float(__byte_perm((w), 0x4B000000u, (sel))), (s_), (c_))
+            const float tn0 = fmaxf(fmaxf(DRB_PLANE(w0, selx, sx, cnx), DRB_PLANE(w1, sely, sy, cny)), fmaxf(DRB_PLANE(w2, selz, sz, cnz), 0.0f));
+            const float tf0 = fminf(fminf(DRB_PLANE(w0, selx ^ 0x22u, sx, cfx), DRB_PLANE(w1, sely ^ 0x22u, sy, cfy)),
+                                    fminf(DRB_PLANE(w2, selz ^ 0x22u, sz, cfz), best));
+            const float tn1 = fmaxf(fmaxf(DRB_PLANE(w3, selx, sx, cnx), DRB_PLANE(w4, sely, sy, cny)), fmaxf(DRB_PLANE(w5, selz, sz, cnz), 0.0f));
+            const float tf1 = fminf(fminf(DRB_PLANE(w3, selx ^ 0x22u, sx, cfx), DRB_PLANE(w4, sely ^ 0x22u, sy, cfy)),
+                                    fminf(DRB_PLANE(w5, selz ^ 0x22u, sz, cfz), best));
+#undef DRB_PLANE
+            const bool h0 = tn0 <= tf0;
+            const bool h1 = tn1 <= tf1;
             if (h0 && h1) {
                 const bool swap = tn1 < tn0;
                 DRB_PUSH(swap ? link.x : link.y);
@@ -735,6 +739,7 @@ int ensure_buffers(drb_scene* s, size_t slots)
 DevScene dev_scene(const drb_scene* s)
 {
     DevScene d;
+    for (int a = 0; a < 3; ++a) drb_quant_grid(s->info.bounds_min[a], s->info.bounds_max[a], &d.qlo[a], &d.qscale[a]);
     d.nodes = s->nodes; d.prims = s->prims; d.recs = s->recs; d.textures = s->textures;
     d.nprims = (int)s->nprims; d.ntextures = s->ntextures;
     return d;

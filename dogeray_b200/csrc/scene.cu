@@ -9,7 +9,7 @@
 //   63-bit Morton key of the box centre -> stable radix sort of (key, slot)
 //   Karras 2012 hierarchy over the sorted keys (ties broken by position)
 //   bottom-up refit with one atomic flag per internal node
-//   emit 64 B nodes that carry both child boxes
+//   emit 32 B nodes that carry both child boxes, quantised to 16 bits on a scene-wide grid
 // All floating-point steps that feed integer outputs (keys) use single IEEE operations (this TU is
 // compiled with -fmad=false), so oracle/lbvh_host.c reproduces keys, order and topology bit-exactly.
 #include "drb_internal.h"
@@ -341,11 +341,30 @@ __global__ void k_ploc_init(int n, const float4* __restrict__ lmin, const float4
     cmin[i] = lo; cmax[i] = lmax[i];
 }
 
+// both planes of one axis of a child box -> min_q | max_q << 16, rounded outwards + 1 quantum
+__device__ __forceinline__ uint32_t quant_axis(float lo, float hi, float qlo, float qscale)
+{
+    int a = (int)floorf((lo - qlo) / qscale) - 1;
+    int b = (int)ceilf((hi - qlo) / qscale) + 1;
+    a = max(0, min(65535, a)); b = max(0, min(65535, b));
+    return (uint32_t)a | ((uint32_t)b << 16);
+}
+__device__ __forceinline__ void quant_child(const float4& lo, const float4& hi, const int* __restrict__ scene_bounds, uint32_t out[3])
+{
+    const float l[3] = { lo.x, lo.y, lo.z }, h[3] = { hi.x, hi.y, hi.z };
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float qlo, qs;
+        drb_quant_grid(ordered_to_float(scene_bounds[a]), ordered_to_float(scene_bounds[3 + a]), &qlo, &qs);
+        out[a] = quant_axis(l[a], h[a], qlo, qs);
+    }
+}
+
 // final labelling: node created k-th becomes (n - 2) - k, so the root is node 0 and parents precede children
 __global__ void k_emit_relabelled(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
                                   const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
-                                  BvhNode* __restrict__ nodes, int32_t* __restrict__ fleft, int32_t* __restrict__ fright,
-                                  float4* __restrict__ fmin, float4* __restrict__ fmax)
+                                  const int* __restrict__ scene_bounds, BvhNode* __restrict__ nodes, int32_t* __restrict__ fleft,
+                                  int32_t* __restrict__ fright, float4* __restrict__ fmin, float4* __restrict__ fmax)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -355,10 +374,9 @@ __global__ void k_emit_relabelled(int n, const float4* __restrict__ lmin, const 
     const int dst = (n - 2) - i;
     const int flc = lc < 0 ? lc : (n - 2) - lc, frc = rc < 0 ? rc : (n - 2) - rc;
     BvhNode nd;
-    nd.c0xy = make_float4(a0.x, a1.x, a0.y, a1.y);
-    nd.c1xy = make_float4(b0.x, b1.x, b0.y, b1.y);
-    nd.cz = make_float4(a0.z, a1.z, b0.z, b1.z);
-    nd.link = make_int4(flc, frc, 0, 0);
+    quant_child(a0, a1, scene_bounds, nd.c0);
+    quant_child(b0, b1, scene_bounds, nd.c1);
+    nd.link[0] = flc; nd.link[1] = frc;
     nodes[dst] = nd;
     fleft[dst] = flc; fright[dst] = frc;
     fmin[dst] = node_min[i]; fmax[dst] = node_max[i];
@@ -366,7 +384,7 @@ __global__ void k_emit_relabelled(int n, const float4* __restrict__ lmin, const 
 
 __global__ void k_emit_nodes(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
                              const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
-                             BvhNode* __restrict__ nodes)
+                             const int* __restrict__ scene_bounds, BvhNode* __restrict__ nodes)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -374,22 +392,20 @@ __global__ void k_emit_nodes(int n, const float4* __restrict__ lmin, const float
     const float4 a0 = lc < 0 ? lmin[~lc] : node_min[lc], a1 = lc < 0 ? lmax[~lc] : node_max[lc];
     const float4 b0 = rc < 0 ? lmin[~rc] : node_min[rc], b1 = rc < 0 ? lmax[~rc] : node_max[rc];
     BvhNode nd;
-    nd.c0xy = make_float4(a0.x, a1.x, a0.y, a1.y);
-    nd.c1xy = make_float4(b0.x, b1.x, b0.y, b1.y);
-    nd.cz = make_float4(a0.z, a1.z, b0.z, b1.z);
-    nd.link = make_int4(lc, rc, 0, 0);
+    quant_child(a0, a1, scene_bounds, nd.c0);
+    quant_child(b0, b1, scene_bounds, nd.c1);
+    nd.link[0] = lc; nd.link[1] = rc;
     nodes[i] = nd;
 }
 
 // a tree of one primitive: child0 = the leaf, child1 = an empty box
-__global__ void k_emit_single(const float4* __restrict__ lmin, const float4* __restrict__ lmax, BvhNode* __restrict__ nodes)
+__global__ void k_emit_single(const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int* __restrict__ scene_bounds,
+                              BvhNode* __restrict__ nodes)
 {
-    const float4 a0 = lmin[0], a1 = lmax[0];
     BvhNode nd;
-    nd.c0xy = make_float4(a0.x, a1.x, a0.y, a1.y);
-    nd.c1xy = make_float4(3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f);
-    nd.cz = make_float4(a0.z, a1.z, 3.0e38f, -3.0e38f);
-    nd.link = make_int4(~0, ~0, 0, 0);
+    quant_child(lmin[0], lmax[0], scene_bounds, nd.c0);
+    nd.c1[0] = nd.c1[1] = nd.c1[2] = 0x0000FFFFu;        // min 65535 > max 0: never hit
+    nd.link[0] = ~0; nd.link[1] = ~0;
     nodes[0] = nd;
 }
 
@@ -520,7 +536,7 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
             k_refit<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent, visits,
                                                        s->dbg.node_min, s->dbg.node_max, d_height);
             if (s->build_flags & DRB_BUILD_LBVH_ONLY) {
-                k_emit_nodes<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.node_min, s->dbg.node_max, s->nodes);
+                k_emit_nodes<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.node_min, s->dbg.node_max, d_bounds, s->nodes);
                 DRB_CUDA(cudaMemcpyAsync(s->tree.left, s->dbg.left, nint * 4, cudaMemcpyDeviceToDevice, st));
                 DRB_CUDA(cudaMemcpyAsync(s->tree.right, s->dbg.right, nint * 4, cudaMemcpyDeviceToDevice, st));
                 DRB_CUDA(cudaMemcpyAsync(s->tree.node_min, s->dbg.node_min, nint * 16, cudaMemcpyDeviceToDevice, st));
@@ -563,7 +579,7 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
                     node_base += tot[1]; n = tot[0]; cur ^= 1;
                 }
                 s->info.rebuild_iterations = iters;
-                k_emit_relabelled<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, pl, pr, pmin, pmax, s->nodes, s->tree.left, s->tree.right,
+                k_emit_relabelled<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, pl, pr, pmin, pmax, d_bounds, s->nodes, s->tree.left, s->tree.right,
                                                                           s->tree.node_min, s->tree.node_max);
                 float4 rootbox;
                 DRB_CUDA(cudaMemcpyAsync(&rootbox, pmin + (nprims - 2), sizeof rootbox, cudaMemcpyDeviceToHost, st));
@@ -571,7 +587,7 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
                 memcpy(&height, &rootbox.w, 4);
             }
         } else {
-            k_emit_single<<<1, 1, 0, st>>>(lmin, lmax, s->nodes);
+            k_emit_single<<<1, 1, 0, st>>>(lmin, lmax, d_bounds, s->nodes);
             height = 1;
         }
         int hb[6];
