@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall,-Wno-unused-function,-pthread",
     "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
-]
+] + os.environ.get("DRB_NVCC_EXTRA", "").split()      # e.g. -DDRB_TRACE_STEPS=3 for tuning experiments
 
 
 def _digest():

@@ -34,8 +34,11 @@
 
 namespace {
 
-constexpr int kStackSize = 100;         // > kMaxTreeHeight in scene.cu (+ the sentinel)
-constexpr int kSmemStack = 32;          // levels of the traversal stack kept in shared memory
+constexpr int kTraceThreads = 128;
+#ifndef DRB_TRACE_STEPS
+#define DRB_TRACE_STEPS 2
+#endif
+constexpr int kSteps = DRB_TRACE_STEPS;   // descent steps per lane between two rounds of warp votes
 constexpr uint32_t kInvalidPid = 0xFFFFFFFFu;
 constexpr float kTMax = 10000.0f;       // singlehit's mindist / aabb2's t_max, kernel.cu:246, 435
 constexpr float kEps = 0.0001f;         // hit_tri's EPSILON, kernel.cu:283
@@ -193,6 +196,14 @@ DRB_D void intersect_prim(const Prim* __restrict__ prims, int slot, const f3& o,
     }
 }
 
+// the float 2^23 + q for the 16-bit half of `w` that `sel` names: bytes (q.lo, q.hi, 0x00, 0x4B)
+DRB_D float prmt_exp23(uint32_t w, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel));
+    return __uint_as_float(r);
+}
+
 constexpr int kSentinel = (int)0x80000000;     // bottom of every traversal stack: "this lane has no ray in flight"
 
 // Persistent traversal with per-lane dynamic ray fetch (after Aila & Laine, "Understanding the Efficiency of
@@ -204,7 +215,7 @@ constexpr int kSentinel = (int)0x80000000;     // bottom of every traversal stac
 // the idle lanes claim fresh rays from the queue with ONE atomic per warp (ballot + popc + shfl), so warps
 // stay populated until the queue runs dry.  (A while-while variant measured slower on B200: with
 // one-primitive leaves, lanes that reach a leaf wait for the slowest descent.)
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Queues q, int cur, int refill, int leaf_batch, int step_min,
+__global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, float scene_scale, Queues q, int cur, int refill, int leaf_batch, int step_min,
                                                const uint32_t* __restrict__ order)
 {
     const uint32_t count = q.counters[cur];
@@ -220,17 +231,15 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Q
     f3 o = mk3(0.f), d = mk3(0.f);
     // per-ray plane constants: t = fma(2^23 + q, s*, c*), near / far plane picked by the PRMT selectors
     float sx = 0.f, sy = 0.f, sz = 0.f, cnx = 0.f, cny = 0.f, cnz = 0.f, cfx = 0.f, cfy = 0.f, cfz = 0.f;
-    uint32_t selx = 0x7410u, sely = 0x7410u, selz = 0x7410u;   // near-plane selector; far = near ^ 0x22
+    uint32_t snx = 0x7410u, sny = 0x7410u, snz = 0x7410u, sfx = 0x7432u, sfy = 0x7432u, sfz = 0x7432u;   // PRMT selectors of the near / far plane
     float best = kTMax; int bestp = -1;
-    // short stack in shared memory, [level][thread]: every lane owns a bank, so pushes and pops at different
-    // depths are still one conflict-free wavefront per warp (a local-memory stack costs one L1 wavefront per
-    // distinct depth).  Levels beyond kSmemStack spill to local memory (trees taller than 32 are rare).
-    __shared__ int s_stack[kSmemStack][128];
-    int spill[kStackSize - kSmemStack];
-    int sp = 0;
-    const unsigned tid = threadIdx.x;
-#define DRB_PUSH(v) do { const int v__ = (v); if (sp < kSmemStack) s_stack[sp][tid] = v__; else spill[sp - kSmemStack] = v__; ++sp; } while (0)
-#define DRB_POP() (--sp, sp < kSmemStack ? s_stack[sp][tid] : spill[sp - kSmemStack])
+    // traversal stack in dynamic shared memory, [level][thread], sized by the host to the tree height + 2: every
+    // lane owns a bank, so pushes and pops at different depths are still one conflict-free wavefront per warp
+    // (a local-memory stack costs one L1 wavefront per distinct depth), and there is no spill path.
+    extern __shared__ int s_stack[];
+    int* sp = s_stack + threadIdx.x;                // points at the next free slot of this lane's column
+#define DRB_PUSH(v) do { *sp = (v); sp += 128; } while (0)
+#define DRB_POP() (sp -= 128, *sp)
 
     for (;;) {
         // ---- refill idle lanes ----------------------------------------------------------------------
@@ -265,27 +274,28 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Q
                         cnx = fmaf(-8388608.0f, sx, (sc.qlo[0] - o.x - px) * ix); cfx = fmaf(-8388608.0f, sx, (sc.qlo[0] - o.x + px) * ix);
                         cny = fmaf(-8388608.0f, sy, (sc.qlo[1] - o.y - py) * iy); cfy = fmaf(-8388608.0f, sy, (sc.qlo[1] - o.y + py) * iy);
                         cnz = fmaf(-8388608.0f, sz, (sc.qlo[2] - o.z - pz) * iz); cfz = fmaf(-8388608.0f, sz, (sc.qlo[2] - o.z + pz) * iz);
-                        selx = ix >= 0.f ? 0x7410u : 0x7432u; sely = iy >= 0.f ? 0x7410u : 0x7432u; selz = iz >= 0.f ? 0x7410u : 0x7432u;
+                        snx = ix >= 0.f ? 0x7410u : 0x7432u; sny = iy >= 0.f ? 0x7410u : 0x7432u; snz = iz >= 0.f ? 0x7410u : 0x7432u;
+                        sfx = snx ^ 0x22u; sfy = sny ^ 0x22u; sfz = snz ^ 0x22u;
                         best = kTMax; bestp = -1;
-                        sp = 0; DRB_PUSH(kSentinel);
+                        sp = s_stack + threadIdx.x; DRB_PUSH(kSentinel);
                         node = 0;
                     }
                 }
             }
         }
-        // ---- one traversal step per lane --------------------------------------------------------------
+        // ---- kSteps descent steps per lane between warp votes ----------------------------------------------
+#pragma unroll
+        for (int step = 0; step < kSteps; ++step) {
         if (node >= 0) {
             const f8 nd = ldg256(sc.nodes + node);                    // the whole node: one 256-bit load
             const uint32_t w0 = __float_as_uint(nd.lo.x), w1 = __float_as_uint(nd.lo.y), w2 = __float_as_uint(nd.lo.z);
             const uint32_t w3 = __float_as_uint(nd.lo.w), w4 = __float_as_uint(nd.hi.x), w5 = __float_as_uint(nd.hi.y);
             const int2 link = make_int2(__float_as_int(nd.hi.z), __float_as_int(nd.hi.w));
-#define DRB_PLANE(w, sel, s_, c_) fmaf(__uint_as_float(__byte_perm((w), 0x4B000000u, (sel))), (s_), (c_))
-            const float tn0 = fmaxf(fmaxf(DRB_PLANE(w0, selx, sx, cnx), DRB_PLANE(w1, sely, sy, cny)), fmaxf(DRB_PLANE(w2, selz, sz, cnz), 0.0f));
-            const float tf0 = fminf(fminf(DRB_PLANE(w0, selx ^ 0x22u, sx, cfx), DRB_PLANE(w1, sely ^ 0x22u, sy, cfy)),
-                                    fminf(DRB_PLANE(w2, selz ^ 0x22u, sz, cfz), best));
-            const float tn1 = fmaxf(fmaxf(DRB_PLANE(w3, selx, sx, cnx), DRB_PLANE(w4, sely, sy, cny)), fmaxf(DRB_PLANE(w5, selz, sz, cnz), 0.0f));
-            const float tf1 = fminf(fminf(DRB_PLANE(w3, selx ^ 0x22u, sx, cfx), DRB_PLANE(w4, sely ^ 0x22u, sy, cfy)),
-                                    fminf(DRB_PLANE(w5, selz ^ 0x22u, sz, cfz), best));
+#define DRB_PLANE(w, sel, s_, c_) fmaf(prmt_exp23((w), (sel)), (s_), (c_))
+            const float tn0 = fmaxf(fmaxf(DRB_PLANE(w0, snx, sx, cnx), DRB_PLANE(w1, sny, sy, cny)), fmaxf(DRB_PLANE(w2, snz, sz, cnz), 0.0f));
+            const float tf0 = fminf(fminf(DRB_PLANE(w0, sfx, sx, cfx), DRB_PLANE(w1, sfy, sy, cfy)), fminf(DRB_PLANE(w2, sfz, sz, cfz), best));
+            const float tn1 = fmaxf(fmaxf(DRB_PLANE(w3, snx, sx, cnx), DRB_PLANE(w4, sny, sy, cny)), fmaxf(DRB_PLANE(w5, snz, sz, cnz), 0.0f));
+            const float tf1 = fminf(fminf(DRB_PLANE(w3, sfx, sx, cfx), DRB_PLANE(w4, sfy, sy, cfy)), fminf(DRB_PLANE(w5, sfz, sz, cfz), best));
 #undef DRB_PLANE
             const bool h0 = tn0 <= tf0;
             const bool h1 = tn1 <= tf1;
@@ -297,10 +307,12 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, float scene_scale, Q
             else if (h1) node = link.y;
             else node = DRB_POP();
         }
-        // ---- postponed leaves -------------------------------------------------------------------------
-        // A lane that arrives at a leaf stashes it and keeps descending; the (long, divergent) primitive test
-        // runs for the whole warp at once when enough lanes hold a leaf, or when too few lanes can still step.
+        // a lane that arrives at a leaf stashes it and keeps descending
         if (node < 0 && node != kSentinel && leaf == 0) { leaf = node; node = DRB_POP(); }
+        }
+        // ---- postponed leaves -------------------------------------------------------------------------
+        // The (long, divergent) primitive test runs for the whole warp at once when enough lanes hold a stashed
+        // leaf, or when too few lanes can still step.
         const unsigned mpend = __ballot_sync(0xffffffffu, leaf != 0);
         if (mpend) {
             const unsigned mstep = __ballot_sync(0xffffffffu, node >= 0);
@@ -652,6 +664,7 @@ struct RenderBuffers {
     size_t capacity = 0;                // path slots
     Queues q{};
     int trace_blocks = 0, shade_blocks = 0;
+    size_t trace_smem = 0;              // dynamic shared memory of k_trace: (tree height + 2) stack levels x 128 lanes
     // ray reordering (one sort per bounce): keys / ray indices, double-buffered, + CUB scratch
     uint32_t* sort_keys[2] = { nullptr, nullptr };
     uint32_t* sort_vals[2] = { nullptr, nullptr };
@@ -729,7 +742,9 @@ int ensure_buffers(drb_scene* s, size_t slots)
     rb->capacity = slots;
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, 128, 0));
+    rb->trace_smem = (size_t)(std::max(s->info.max_depth, 1) + 2) * kTraceThreads * sizeof(int);
+    DRB_CUDA(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb->trace_smem));
+    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, kTraceThreads, rb->trace_smem));
     rb->trace_blocks = sms * std::max(per_sm, 1);
     DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 128, 0));
     rb->shade_blocks = sms * std::max(per_sm, 1);
@@ -845,7 +860,7 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
                 }
             }
             if (stats) { auto e0 = pool.get(), e1 = pool.get(); trace_ev.push_back({ e0, e1 }); DRB_CUDA(cudaEventRecord(e0, stream)); }
-            k_trace<<<rb->trace_blocks, 128, 0, stream>>>(sc, fp.scene_scale, q, cur, g_refill, g_leaf_batch, g_step_min, order);
+            k_trace<<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(sc, fp.scene_scale, q, cur, g_refill, g_leaf_batch, g_step_min, order);
             if (stats) DRB_CUDA(cudaEventRecord(trace_ev.back().second, stream));
             k_shade<<<std::min<uint32_t>((uint32_t)rb->shade_blocks, (live + 127u) / 128u), 128, 0, stream>>>(sc, fp, q, cur, b == st->max_depth - 1 ? 1 : 0);
             k_prepare<<<1, 32, 0, stream>>>(q.counters, cur, -1, 0u);
@@ -986,7 +1001,7 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     const uint32_t nn = (uint32_t)n;
     k_load_rays<<<(nn + 255) / 256, 256, 0, stream>>>(d_o, d_d, nn, q);
     k_prepare<<<1, 32, 0, stream>>>(q.counters, -1, 0, nn);
-    k_trace<<<rb->trace_blocks, 128, 0, stream>>>(dev_scene(s), scene_scale(s), q, 0, g_refill, g_leaf_batch, g_step_min, nullptr);
+    k_trace<<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(dev_scene(s), scene_scale(s), q, 0, g_refill, g_leaf_batch, g_step_min, nullptr);
     k_store_ids<<<(nn + 255) / 256, 256, 0, stream>>>(q.hit, s->orig_id, nn, d_ids, d_t);
     cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
     if (t) cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
