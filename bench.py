@@ -304,21 +304,32 @@ def main():
     h2d = hs.num_objects * drb.OBJECT_DTYPE.itemsize
     d2h = st.height * st.width * 3 * 4
 
+    e2e_parts = {"create_ms": 0.0, "render_ms": 0.0, "reduce_readback_ms": 0.0, "free_ms": 0.0}
+
     def step_e2e():
+        t0 = time.perf_counter()
         sc = drb.Scene.from_host(hs, device=local)            # H2D of every object line + GPU LBVH build
+        t1 = time.perf_counter()
         s = sc.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, stream=stream, want_stats=True)
+        t2 = time.perf_counter()
         if world > 1:
             dist.reduce(accum, dst=0)
         if rank == 0:
             host_img.copy_(accum, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        t3 = time.perf_counter()
         sc.close()
+        t4 = time.perf_counter()
+        for k, v in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            e2e_parts[k] += v * 1e3
         return s
 
     scene.close()
     for _ in range(min(W, 1)):
         step_e2e()
     barrier()
+    for k in e2e_parts:
+        e2e_parts[k] = 0.0
     t_e = time.perf_counter(); e_rays = 0
     for _ in range(K):
         e_rays += step_e2e().rays
@@ -344,7 +355,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "spp_per_s_1080p": paths_all / (ms_max * 1e-3) / 2073600.0, "rays_per_path": rays_all / max(paths_all, 1.0),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e_ms_max / K,
-                    "what": "per step: upload object lines, GPU LBVH build, render, reduce, float image to pinned host memory"},
+                    "what": "per step: upload object lines, GPU LBVH build, render, reduce, float image to pinned host memory",
+                    "parts_ms_per_step_rank0": {k: v / K for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,

@@ -129,3 +129,11 @@ struct drb_scene {
     } while (0)
 
 void drb_render_buffers_free(drb_scene* s);
+
+// Device memory for scenes and render buffers.  Blocks come from the device's stream-ordered pool (release
+// threshold raised so nothing goes back to the driver) through an exact-size cache: a scene that is created,
+// rendered and freed every frame -- the reference's CudaStarter pattern, kernel.cu:2604-2665 -- finds every block
+// it needs in the cache and performs no allocator call at all.  Blocks must be idle (their stream synchronised)
+// when they are handed back.
+cudaError_t drb_dev_alloc(void** p, size_t bytes, cudaStream_t st);
+void drb_dev_free(void* p, cudaStream_t st);

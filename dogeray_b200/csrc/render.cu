@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_generate(FrameParams fp, uint32_t nslot
     const f3 org = c.from + offset;
     q.ray_o[0][slot] = make_float4(org.x, org.y, org.z, __uint_as_float(slot));
     q.ray_d[0][slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(rng.draws));
-    q.thr[0][slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+    q.thr[0][slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float((uint32_t)x | ((uint32_t)y << 16)));   // pixel rides along: no divisions in k_shade
 }
 
 // ---- closest hit ----------------------------------------------------------------------------------
@@ -172,7 +172,7 @@ DRB_D void intersect_prim(const Prim* __restrict__ prims, int slot, const f3& o,
         const f3 h = cross(d, e2);
         const float a = dot(e1, h);
         if (a > -kEps && a < kEps) return;
-        const float f = 1.0f / a;
+        const float f = __frcp_rn(a);               // correctly rounded 1/a == (float)(1.0 / a) of kernel.cu:293
         const f3 sv = o - v0;
         const float u = f * dot(sv, h);
         if (u < 0.0f || u > 1.0f) return;
@@ -471,10 +471,10 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Q
                         rough = (float)c.x / 255.0f / 2.0f;
                     }
 
-                    int x, y; uint32_t s;
-                    slot_to_pixel(fp, pid, x, y, s);
+                    const uint32_t xy = __float_as_uint(a4.w);
+                    const uint32_t smp = (pid >> 5) % fp.samples;              // slot = ((tile * samples) + s) * 32 + lane
                     PathRng rng;
-                    rng.init(fp.seed, (uint32_t)x, (uint32_t)y, fp.sample_base + s, __float_as_uint(d4.w));
+                    rng.init(fp.seed, xy & 0xFFFFu, xy >> 16, fp.sample_base + smp, __float_as_uint(d4.w));
 
                     f3 ndir = raydir;
                     alive = true;
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Q
                     if (alive) {
                         no = make_float4(hitpoint.x, hitpoint.y, hitpoint.z, o4.w);
                         nd = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(rng.draws));
-                        nt = make_float4(atten.x, atten.y, atten.z, 0.f);
+                        nt = make_float4(atten.x, atten.y, atten.z, a4.w);
                     }
                 }
             }
@@ -723,20 +723,20 @@ int ensure_buffers(drb_scene* s, size_t slots)
     Queues& q = rb->q;
     cudaStream_t st = s->stream;
     for (int k = 0; k < 2; ++k) {
-        DRB_CUDA(cudaMallocAsync((void**)&q.ray_o[k], slots * sizeof(float4), st));
-        DRB_CUDA(cudaMallocAsync((void**)&q.ray_d[k], slots * sizeof(float4), st));
-        DRB_CUDA(cudaMallocAsync((void**)&q.thr[k], slots * sizeof(float4), st));
+        DRB_CUDA(drb_dev_alloc((void**)&q.ray_o[k], slots * sizeof(float4), st));
+        DRB_CUDA(drb_dev_alloc((void**)&q.ray_d[k], slots * sizeof(float4), st));
+        DRB_CUDA(drb_dev_alloc((void**)&q.thr[k], slots * sizeof(float4), st));
     }
-    DRB_CUDA(cudaMallocAsync((void**)&q.hit, slots * sizeof(uint2), st));
-    DRB_CUDA(cudaMallocAsync((void**)&q.contrib, slots * sizeof(float4), st));
-    DRB_CUDA(cudaMallocAsync((void**)&q.counters, CNT_WORDS * sizeof(uint32_t), st));
+    DRB_CUDA(drb_dev_alloc((void**)&q.hit, slots * sizeof(uint2), st));
+    DRB_CUDA(drb_dev_alloc((void**)&q.contrib, slots * sizeof(float4), st));
+    DRB_CUDA(drb_dev_alloc((void**)&q.counters, CNT_WORDS * sizeof(uint32_t), st));
     for (int k = 0; k < 2; ++k) {
-        DRB_CUDA(cudaMallocAsync((void**)&rb->sort_keys[k], slots * sizeof(uint32_t), st));
-        DRB_CUDA(cudaMallocAsync((void**)&rb->sort_vals[k], slots * sizeof(uint32_t), st));
+        DRB_CUDA(drb_dev_alloc((void**)&rb->sort_keys[k], slots * sizeof(uint32_t), st));
+        DRB_CUDA(drb_dev_alloc((void**)&rb->sort_vals[k], slots * sizeof(uint32_t), st));
     }
     DRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, rb->sort_tmp_bytes, rb->sort_keys[0], rb->sort_keys[1], rb->sort_vals[0], rb->sort_vals[1],
                                              (int)std::min<size_t>(slots, 0x7FFFFFFF), 0, 24, st));
-    DRB_CUDA(cudaMallocAsync(&rb->sort_tmp, rb->sort_tmp_bytes ? rb->sort_tmp_bytes : 16, st));
+    DRB_CUDA(drb_dev_alloc(&rb->sort_tmp, rb->sort_tmp_bytes ? rb->sort_tmp_bytes : 16, st));
     DRB_CUDA(cudaMemsetAsync(q.counters, 0, CNT_WORDS * sizeof(uint32_t), st));
     DRB_CUDA(cudaStreamSynchronize(st));             // the buffers may be used from a caller-provided stream next
     rb->capacity = slots;
@@ -899,10 +899,10 @@ void drb_render_buffers_free(drb_scene* s)
     Queues& q = s->rb->q;
     cudaStream_t st = s->stream;
     cudaDeviceSynchronize();                          // renders may have run on caller streams
-    for (int k = 0; k < 2; ++k) { cudaFreeAsync(q.ray_o[k], st); cudaFreeAsync(q.ray_d[k], st); cudaFreeAsync(q.thr[k], st); }
-    cudaFreeAsync(q.hit, st); cudaFreeAsync(q.contrib, st); cudaFreeAsync(q.counters, st);
-    for (int k = 0; k < 2; ++k) { cudaFreeAsync(s->rb->sort_keys[k], st); cudaFreeAsync(s->rb->sort_vals[k], st); }
-    cudaFreeAsync(s->rb->sort_tmp, st);
+    for (int k = 0; k < 2; ++k) { drb_dev_free(q.ray_o[k], st); drb_dev_free(q.ray_d[k], st); drb_dev_free(q.thr[k], st); }
+    drb_dev_free(q.hit, st); drb_dev_free(q.contrib, st); drb_dev_free(q.counters, st);
+    for (int k = 0; k < 2; ++k) { drb_dev_free(s->rb->sort_keys[k], st); drb_dev_free(s->rb->sort_vals[k], st); }
+    drb_dev_free(s->rb->sort_tmp, st);
     delete s->rb;
     s->rb = nullptr;
 }
@@ -931,7 +931,7 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
     float* d = nullptr;
     drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
-    DRB_CUDA(cudaMallocAsync((void**)&d, n * sizeof(float), stream));
+    DRB_CUDA(drb_dev_alloc((void**)&d, n * sizeof(float), stream));
     int rc = DRB_OK;
     if (o.flags & DRB_FLAG_ACCUMULATE) {
         if (cudaMemcpyAsync(d, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DRB_ERR_CUDA;
@@ -942,7 +942,8 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) { drb_set_error("download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
     }
-    cudaFreeAsync(d, stream);
+    cudaStreamSynchronize(stream);
+    drb_dev_free(d, stream);
     return rc;
 }
 
@@ -960,8 +961,8 @@ int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opt
     const uint32_t spp = o.sample_count ? o.sample_count : (uint32_t)std::max(settings->spp, 0);
     float* d_acc = nullptr; int32_t* d_out = nullptr;
     const size_t nfull = (size_t)settings->width * settings->height * 3;
-    DRB_CUDA(cudaMallocAsync((void**)&d_acc, (size_t)W * H * 3 * sizeof(float), stream));
-    if (cudaMallocAsync((void**)&d_out, nfull * sizeof(int32_t), stream) != cudaSuccess) { cudaFreeAsync(d_acc, stream); drb_set_error("out of device memory"); return DRB_ERR_NOMEM; }
+    DRB_CUDA(drb_dev_alloc((void**)&d_acc, (size_t)W * H * 3 * sizeof(float), stream));
+    if (drb_dev_alloc((void**)&d_out, nfull * sizeof(int32_t), stream) != cudaSuccess) { drb_dev_free(d_acc, stream); drb_set_error("out of device memory"); return DRB_ERR_NOMEM; }
     int rc = DRB_OK;
     {
         // entries outside the launched grid stay as the caller left them
@@ -977,7 +978,8 @@ int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opt
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) { drb_set_error("frame download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
     }
-    cudaFreeAsync(d_acc, stream); cudaFreeAsync(d_out, stream);
+    cudaStreamSynchronize(stream);
+    drb_dev_free(d_acc, stream); drb_dev_free(d_out, stream);
     return rc;
 }
 
@@ -992,10 +994,10 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     Queues q = rb->q;
     cudaStream_t stream = s->stream;
     float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int32_t* d_ids = nullptr;
-    DRB_CUDA(cudaMallocAsync((void**)&d_o, (size_t)n * 12, stream));
-    DRB_CUDA(cudaMallocAsync((void**)&d_d, (size_t)n * 12, stream));
-    DRB_CUDA(cudaMallocAsync((void**)&d_t, (size_t)n * 4, stream));
-    DRB_CUDA(cudaMallocAsync((void**)&d_ids, (size_t)n * 4, stream));
+    DRB_CUDA(drb_dev_alloc((void**)&d_o, (size_t)n * 12, stream));
+    DRB_CUDA(drb_dev_alloc((void**)&d_d, (size_t)n * 12, stream));
+    DRB_CUDA(drb_dev_alloc((void**)&d_t, (size_t)n * 4, stream));
+    DRB_CUDA(drb_dev_alloc((void**)&d_ids, (size_t)n * 4, stream));
     cudaMemcpyAsync(d_o, o3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_d, d3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
     const uint32_t nn = (uint32_t)n;
@@ -1007,7 +1009,7 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     if (t) cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFreeAsync(d_o, stream); cudaFreeAsync(d_d, stream); cudaFreeAsync(d_t, stream); cudaFreeAsync(d_ids, stream);
+    drb_dev_free(d_o, stream); drb_dev_free(d_d, stream); drb_dev_free(d_t, stream); drb_dev_free(d_ids, stream);
     if (e != cudaSuccess) { drb_set_error("drb_trace_ids: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
     return DRB_OK;
 }
@@ -1028,15 +1030,15 @@ int drb_primary_rays(drb_scene* s, const drb_settings* settings, const drb_opts*
     cudaStream_t stream = s->stream;
     const size_t n = (size_t)W * H * 3;
     float *d_o = nullptr, *d_d = nullptr;
-    DRB_CUDA(cudaMallocAsync((void**)&d_o, n * 4, stream));
-    DRB_CUDA(cudaMallocAsync((void**)&d_d, n * 4, stream));
+    DRB_CUDA(drb_dev_alloc((void**)&d_o, n * 4, stream));
+    DRB_CUDA(drb_dev_alloc((void**)&d_d, n * 4, stream));
     k_generate<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q);
     k_store_rays<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q, d_o, d_d);
     cudaMemcpyAsync(o3, d_o, n * 4, cudaMemcpyDeviceToHost, stream);
     cudaMemcpyAsync(d3, d_d, n * 4, cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFreeAsync(d_o, stream); cudaFreeAsync(d_d, stream);
+    drb_dev_free(d_o, stream); drb_dev_free(d_d, stream);
     if (e != cudaSuccess) { drb_set_error("drb_primary_rays: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
     return DRB_OK;
 }

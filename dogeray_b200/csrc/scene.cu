@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 namespace {
 
@@ -417,7 +419,7 @@ template <typename T> int dev_alloc(T** p, size_t count, cudaStream_t st)
 {
     *p = nullptr;
     if (count == 0) count = 1;
-    DRB_CUDA(cudaMallocAsync((void**)p, count * sizeof(T), st));
+    DRB_CUDA(drb_dev_alloc((void**)p, count * sizeof(T), st));
     return DRB_OK;
 }
 
@@ -425,7 +427,7 @@ struct Scratch {
     cudaStream_t st;
     std::vector<void*> ptrs;
     explicit Scratch(cudaStream_t s) : st(s) {}
-    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+    ~Scratch() { cudaStreamSynchronize(st); for (void* p : ptrs) drb_dev_free(p, st); }   // blocks must be idle when handed back
     template <typename T> int alloc(T** p, size_t count)
     {
         int rc = dev_alloc(p, count, st);
@@ -433,6 +435,63 @@ struct Scratch {
         return rc;
     }
 };
+
+} // namespace
+
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::unordered_map<void*, size_t> live;                     // every block handed out -> its size
+    std::unordered_multimap<size_t, void*> idle[16];            // per device: size -> idle blocks
+    size_t idle_bytes[16] = { 0 };
+    static constexpr size_t kMaxIdleBytes = size_t(48) << 30;   // beyond this, blocks go back to the pool
+} g_cache;
+}
+
+cudaError_t drb_dev_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes == 0) bytes = 16;
+    {
+        std::lock_guard<std::mutex> g(g_cache.mu);
+        auto& idle = g_cache.idle[dev & 15];
+        auto it = idle.find(bytes);
+        if (it != idle.end()) {
+            *p = it->second;
+            idle.erase(it);
+            g_cache.idle_bytes[dev & 15] -= bytes;
+            g_cache.live[*p] = bytes;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(p, bytes, st);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> g(g_cache.mu);
+    g_cache.live[*p] = bytes;
+    return cudaSuccess;
+}
+
+void drb_dev_free(void* p, cudaStream_t st)
+{
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> g(g_cache.mu);
+        auto it = g_cache.live.find(p);
+        if (it != g_cache.live.end()) { bytes = it->second; g_cache.live.erase(it); }
+        if (bytes && g_cache.idle_bytes[dev & 15] + bytes <= BlockCache::kMaxIdleBytes) {
+            g_cache.idle[dev & 15].emplace(bytes, p);
+            g_cache.idle_bytes[dev & 15] += bytes;
+            return;
+        }
+    }
+    cudaFreeAsync(p, st);
+}
+
+namespace {
 
 int retain_pool(int device)
 {
@@ -630,7 +689,7 @@ int upload_textures(drb_scene* s, const drb_host_scene* hs)
             continue;                                   // the reference loads every .ppm it finds; unused ones may be anything
         }
         void* d = nullptr;
-        DRB_CUDA(cudaMallocAsync(&d, img.rgba.size(), s->stream));
+        DRB_CUDA(drb_dev_alloc(&d, img.rgba.size(), s->stream));
         s->texture_storage.push_back(d);
         DRB_CUDA(cudaMemcpyAsync(d, img.rgba.data(), img.rgba.size(), cudaMemcpyHostToDevice, s->stream));
         DRB_CUDA(cudaStreamSynchronize(s->stream));      // img goes out of scope
@@ -665,12 +724,13 @@ void drb_scene_free(drb_scene* s)
     cudaSetDevice(s->device);
     drb_render_buffers_free(s);
     cudaStream_t st = s->stream;
+    if (st) cudaStreamSynchronize(st);
     for (void* p : { (void*)s->nodes, (void*)s->prims, (void*)s->recs, (void*)s->orig_id, (void*)s->textures, (void*)s->dbg.keys,
                      (void*)s->dbg.order, (void*)s->dbg.parent, (void*)s->dbg.left, (void*)s->dbg.right, (void*)s->dbg.node_min,
                      (void*)s->dbg.node_max, (void*)s->tree.left, (void*)s->tree.right, (void*)s->tree.node_min, (void*)s->tree.node_max })
-        if (p) cudaFreeAsync(p, st);
-    for (void* p : s->texture_storage) cudaFreeAsync(p, st);
-    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        if (p) drb_dev_free(p, st);
+    for (void* p : s->texture_storage) drb_dev_free(p, st);
+    if (st) cudaStreamDestroy(st);
     delete s;
 }
 
