@@ -44,6 +44,9 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+WORKLOAD_TEXTURES = []
+
+
 def workload(name):
     from dogeray_b200 import synth
     if name == "grid1m":
@@ -52,6 +55,15 @@ def workload(name):
     elif name == "bunny":
         objs, st = synth.bunny_class_scene(width=1920, height=1080, spp=64, max_depth=8)
         desc = "bunny-class stand-in (3 x 81920-tri blobs + floor + wall; sanford.blend.rts is a missing blob), 1920x1080, 64 spp, 8 bounces"
+    elif name == "city10m":
+        objs, st = synth.city_scene(width=3840, height=2160, spp=1024, max_depth=10)
+        desc = "synthetic ~10M-triangle city grid, 3840x2160, 1024 spp, 10 bounces (BASELINE config 5 stand-in)"
+    elif name == "mats":
+        import tempfile
+        d = tempfile.mkdtemp(prefix="drb_tex_")
+        objs, st, tex = synth.materials_scene(synth.write_test_textures(d))
+        WORKLOAD_TEXTURES[:] = tex
+        desc = "material/texture/env-map divergence scene (10 material classes, 92k triangles), 1920x1080, 256 spp, 10 bounces (BASELINE config 4 stand-in)"
     elif name == "cube":
         objs, st = synth.heightfield_scene(n=8, width=256, height=256, spp=16, max_depth=4)
         desc = "small smoke workload, 256x256, 16 spp, 4 bounces"
@@ -254,7 +266,7 @@ def main():
     dev = torch.device("cuda", local)
 
     t0 = time.time()
-    hs = drb.HostScene.from_objects(objs, st)
+    hs = drb.HostScene.from_objects(objs, st, WORKLOAD_TEXTURES)
     scene = drb.Scene.from_host(hs, device=local)
     bi = scene.build_info
     log("[rank %d] scene: %d prims, %d nodes, height %d, upload %.1f ms, GPU LBVH build %.1f ms (host wall %.2f s)" %

@@ -74,6 +74,13 @@ def build(force=False, verbose=False):
     if verbose:
         print("+", " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
+    # headless CLI, the drop-in for `raygpu.exe scene.rts`
+    cli = os.path.join(HERE, "dogeray-b200")
+    cmd = ["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(CSRC, "cli.cpp"), "-o", cli,
+           "-L" + HERE, "-ldogeray_b200", "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print("+", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
     with open(STAMP, "w") as f:
         f.write(dig)
     return OUT

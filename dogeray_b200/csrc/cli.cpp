@@ -1,0 +1,79 @@
+// dogeray-b200: headless drop-in for `raygpu.exe [scene.rts]` (raygpu/kernel.cu:2021-2051, 2486-2516).
+//
+//   dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]
+//
+// Like the reference it opens `scene.rts` when no path is given, looks for textures among the *.ppm files of the
+// current working directory, and writes `<scene path>.bmp` (the file SPACE exports, 32-bpp V4 header).  Unlike the
+// reference there is no window: it renders the settings line's samples per pixel once and exits.
+#include "dogeray_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static int fail(const char* what)
+{
+    fprintf(stderr, "dogeray-b200: %s: %s\n", what, drb_last_error());
+    return 1;
+}
+
+int main(int argc, char** argv)
+{
+    std::string scene_path = "scene.rts", out_path;
+    int spp = -1, depth = -1, w = -1, h = -1, device = 0;
+    unsigned long long seed = 0;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { fprintf(stderr, "dogeray-b200: %s needs a value\n", name); exit(2); }
+            return argv[++i];
+        };
+        if (a == "--spp") spp = atoi(next("--spp"));
+        else if (a == "--depth") depth = atoi(next("--depth"));
+        else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
+        else if (a == "--device") device = atoi(next("--device"));
+        else if (a == "--out") out_path = next("--out");
+        else if (a == "--res") { if (sscanf(next("--res"), "%dx%d", &w, &h) != 2) { fprintf(stderr, "dogeray-b200: --res wants WxH\n"); return 2; } }
+        else if (a == "-h" || a == "--help") {
+            printf("usage: dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]\n");
+            return 0;
+        } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "dogeray-b200: unknown option %s\n", a.c_str()); return 2; }
+        else scene_path = a;
+    }
+    printf("Opening:%s\n", scene_path.c_str());
+    drb_host_scene* hs = nullptr;
+    if (drb_host_scene_load(scene_path.c_str(), nullptr, &hs) != DRB_OK) return fail("cannot load scene");
+    printf("%lld tris\n%d textures total\n", (long long)drb_host_scene_num_objects(hs), drb_host_scene_num_textures(hs));
+    if (drb_host_scene_num_skipped(hs)) fprintf(stderr, "dogeray-b200: warning: %s\n", drb_last_error());
+    drb_scene* scene = nullptr;
+    printf("Building BVH..\n");
+    if (drb_scene_create(hs, device, &scene) != DRB_OK) return fail("cannot create device scene");
+    drb_build_info bi;
+    drb_scene_build_info(scene, &bi);
+    printf("Done! %lld nodes total (upload %.2f ms, build %.2f ms)\n", (long long)bi.nnodes, bi.upload_ms, bi.build_ms);
+    drb_settings st;
+    drb_scene_settings(scene, &st);
+    if (spp > 0) st.spp = spp;
+    if (depth >= 0) st.max_depth = depth;
+    if (w > 0 && h > 0) { st.width = w; st.height = h; }
+    drb_opts opts;
+    drb_opts_default(&opts);
+    opts.seed = seed;
+    std::vector<float> accum((size_t)st.width * st.height * 3);
+    drb_stats stats;
+    if (drb_render(scene, &st, &opts, accum.data(), &stats) != DRB_OK) return fail("render failed");
+    printf("Time = %.3f ms  %llu samples  %.1f Mrays/s\n", stats.total_ms, (unsigned long long)st.spp,
+           stats.total_ms > 0 ? stats.rays / (stats.total_ms * 1e-3) / 1e6 : 0.0);
+    std::vector<uint8_t> rgb(accum.size());
+    if (drb_tonemap(accum.data(), st.width, st.height, st.spp > 0 ? st.spp : 1, rgb.data()) != DRB_OK) return fail("tonemap failed");
+    if (out_path.empty()) out_path = scene_path + ".bmp";
+    const bool ppm = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".ppm";
+    int rc = ppm ? drb_write_ppm(out_path.c_str(), rgb.data(), st.width, st.height) : drb_write_bmp(out_path.c_str(), rgb.data(), st.width, st.height);
+    if (rc != DRB_OK) return fail("cannot write image");
+    printf("exported image:%s\n", out_path.c_str());
+    drb_scene_free(scene);
+    drb_host_scene_free(hs);
+    return 0;
+}

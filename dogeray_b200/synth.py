@@ -218,3 +218,62 @@ def heightfield_scene(n=64, size=8.0, amp=0.6, width=256, height=256, spp=4, max
     st.look[:] = [0.0, 0.0, 0.0]
     st.max_depth, st.spp, st.width, st.height = max_depth, spp, width, height
     return objs, st
+
+
+def write_test_textures(directory: str):
+    """Two small procedural .ppm files (P6, as plugin/rtsexport.py:56-79 writes them): an environment map and a
+    colour/roughness map.  Returns their paths."""
+    import os
+    yy, xx = np.mgrid[0:256, 0:512]
+    env = np.stack([120 + 100 * np.sin(xx / 40.0), 140 + 90 * np.cos(yy / 30.0), 200 + 40 * np.sin((xx + yy) / 25.0)], -1)
+    env[(yy < 40) & (np.abs(xx - 256) < 40)] = 255                          # a bright "sun"
+    tex = np.stack([(xx[:256, :256] // 16 + yy[:256, :256] // 16) % 2 * 180 + 40, 80 + (xx[:256, :256] % 64) * 2, 200 - (yy[:256, :256] % 32) * 4], -1)
+    paths = []
+    for name, img in (("synth_env.ppm", env), ("synth_tex.ppm", tex)):
+        p = os.path.join(directory, name)
+        a = np.clip(img, 0, 255).astype(np.uint8)
+        with open(p, "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (a.shape[1], a.shape[0]) + a.tobytes())
+        paths.append(p)
+    return paths
+
+
+def materials_scene(tex_paths, width=1920, height=1080, spp=256, max_depth=10, nu=96, nv=48):
+    """BASELINE config 4 stand-in (mats + glass + texer with an environment map): a row of blobs, one per material
+    class the reference has -- diffuse, mirror (2), metal (3), glass (4), glossy (5), emissive (1), textured,
+    checker, roughness-mapped metal, smooth-shaded -- on a checkered floor under an environment map.
+    tex_paths: [environment.ppm, texture.ppm] (write_test_textures)."""
+    specs = [
+        dict(mat=0, col=(0.8, 0.8, 0.8)), dict(mat=2, col=(0.95, 0.95, 0.95)), dict(mat=3, col=(0.9, 0.7, 0.3), rough=0.15),
+        dict(mat=4, col=(1.0, 1.0, 1.0), rough=1.45), dict(mat=5, col=(0.3, 0.6, 0.9), rough=0.05), dict(mat=1, col=(3.0, 2.4, 1.8)),
+        dict(mat=0, col=(0.8, 0.8, 0.8), tex=1), dict(mat=0, col=(0.2, 0.7, 0.3), checker=1), dict(mat=3, col=(0.9, 0.9, 0.9), rough=0.3, rtex=1),
+        dict(mat=0, col=(0.85, 0.3, 0.3), smooth=1),
+    ]
+    parts = []
+    for k, sp in enumerate(specs):
+        v0, v1, v2, vn = bumpy_torus(nu, nv, R=1.6, r=0.7, seed=40 + k)
+        off = np.array([(k % 5 - 2) * 5.5, -1.2, (k // 5) * 6.0 - 3.0], np.float32)
+        o = _tri_objects(v0 + off, v1 + off, v2 + off, np.array(sp["col"], np.float32), sp["mat"], sp.get("rough", 0.0),
+                         smooth=sp.get("smooth", 1 if sp["mat"] == 4 else 0), vn=vn)
+        # UVs from the parameter grid so that textures / checker have something to index
+        u = (np.arange(len(o)) % (nu * nv)) / float(nu * nv)
+        o["t1"] = np.stack([u, (u * 7) % 1.0], 1); o["t2"] = o["t1"] + (0.01, 0.0); o["t3"] = o["t1"] + (0.0, 0.01)
+        if sp.get("tex"):
+            o["texnum"] = 1
+        if sp.get("rtex"):
+            o["rtexnum"] = 1
+        if sp.get("checker"):
+            o["checker"] = 1
+        parts.append(o)
+    fl = quad((-40, 0, -40), (40, 0, -40), (40, 0, 40), (-40, 0, 40), (0.6, 0.6, 0.6))
+    fl["checker"] = 1
+    fl["t1"] = (0, 0); fl["t2"] = (4, 0); fl["t3"] = (4, 4)
+    parts.append(fl)
+    objs = np.concatenate(parts)
+    st = default_settings()
+    st.cam[:] = [0.0, -7.0, 17.0]
+    st.look[:] = [0.0, -1.0, 0.0]
+    st.backtex = 0
+    st.bg_intensity = 1.0
+    st.max_depth, st.spp, st.width, st.height = max_depth, spp, width, height
+    return objs, st, list(tex_paths)

@@ -1,0 +1,56 @@
+"""The headless CLI (drop-in for `raygpu.exe scene.rts`, kernel.cu:2041-2051, 2501-2516)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import dogeray_b200 as drb
+from dogeray_b200 import synth
+from conftest import ROOT
+
+CLI = os.path.join(ROOT, "dogeray_b200", "dogeray-b200")
+
+
+def test_cli_help_and_bad_option():
+    p = subprocess.run([CLI, "--help"], capture_output=True, text=True)
+    assert p.returncode == 0 and "usage: dogeray-b200" in p.stdout
+    p = subprocess.run([CLI, "--bogus"], capture_output=True, text=True)
+    assert p.returncode == 2
+
+
+def test_cli_missing_scene_fails_loudly(tmp_path):
+    p = subprocess.run([CLI], capture_output=True, text=True, cwd=tmp_path)       # default scene.rts does not exist here
+    assert p.returncode == 1 and "cannot open scene file" in p.stderr
+
+
+def test_cli_without_gpu_has_no_fallback(tmp_path):
+    if drb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    objs, st = synth.heightfield_scene(n=4, width=16, height=8, spp=1)
+    drb.write_rts(str(tmp_path / "scene.rts"), st, objs)
+    p = subprocess.run([CLI], capture_output=True, text=True, cwd=tmp_path)
+    assert p.returncode == 1 and "no CPU path" in p.stderr
+    assert not os.path.exists(tmp_path / "scene.rts.bmp")
+
+
+@pytest.mark.gpu
+def test_cli_renders_the_same_image_as_the_library(tmp_path):
+    objs, st = synth.heightfield_scene(n=16, width=64, height=40, spp=3, max_depth=4)
+    rng = np.random.default_rng(0)
+    tex = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+    with open(tmp_path / "sky.ppm", "wb") as f:                                      # found through the CWD scan
+        f.write(b"P6\n8 8\n255\n" + tex.tobytes())
+    drb.write_rts(str(tmp_path / "scene.rts"), st, objs, backtex_name="sky.ppm")
+    p = subprocess.run([CLI, "--seed", "9"], capture_output=True, text=True, cwd=tmp_path)     # no path: opens scene.rts
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "exported image:scene.rts.bmp" in p.stdout and "1 textures total" in p.stdout
+    raw = open(tmp_path / "scene.rts.bmp", "rb").read()
+    px = np.frombuffer(raw[122:], np.uint8).reshape(40, 64, 4)[::-1, :, 2::-1]       # bottom-up BGRA -> top-down RGB
+    sc = drb.Scene.load(str(tmp_path / "scene.rts"), str(tmp_path))
+    assert sc.settings.backtex == 0
+    acc, _ = sc.render(sc.settings, seed=9)
+    assert np.array_equal(px, drb.tonemap(acc, 3))
+    p = subprocess.run([CLI, "scene.rts", "--spp", "1", "--res", "32x16", "--out", "o.ppm"], capture_output=True, text=True, cwd=tmp_path)
+    assert p.returncode == 0 and open(tmp_path / "o.ppm", "rb").read().startswith(b"P6\n32 16\n255\n")
