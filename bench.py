@@ -140,6 +140,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class StdoutToStderr:
+    """The reference prints banners to stdout (e.g. "N textures total", kernel.cu:1995); keep our stdout to the one
+    JSON line by pointing file descriptor 1 at stderr while reference code runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def cpu_reference_arm(objs, st, desc, spp_sample, steps, warmup, threads):
     """the reference's host-compiled trace function (or the restatement) on a bounded sample: `spp_sample`
     samples per pixel of the same frame.  Returns (Mrays/s, ms per step, kind, rays per path)."""
@@ -241,8 +258,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        spp_s = args.cpu_spp or 2
-        v, ms, kind, rpp = cpu_reference_arm(objs, st, desc, spp_s, K, W, ncores)
+        spp_s = args.cpu_spp or 8
+        with StdoutToStderr():
+            v, ms, kind, rpp = cpu_reference_arm(objs, st, desc, spp_s, K, W, ncores)
         sample = "%d of %d spp per step on %d host threads (same scene, camera, depth)" % (spp_s, st.spp, ncores)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -381,14 +399,16 @@ def main():
         if world == 1 and not args.no_baselines:
             rpp = rays_all / max(paths_all, 1.0)
             try:
-                spp_s = args.cpu_spp or 2
-                v, cms, kind, _ = cpu_reference_arm(objs, st, desc, spp_s, 1, 0, ncores)
+                spp_s = args.cpu_spp or 8
+                with StdoutToStderr():
+                    v, cms, kind, _ = cpu_reference_arm(objs, st, desc, spp_s, 1, 0, ncores)
                 line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": ncores, "kind": kind,
                                         "sample": "%d of %d spp of the same frame on %d host threads, %.1f s" % (spp_s, st.spp, ncores, cms / 1e3)}
             except Exception as ex:                                  # the baseline must never cost the measurement
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": ncores, "kind": "port", "sample": "failed: %r" % (ex,)}
             try:
-                line["ref_gpu"] = ref_gpu_baseline(objs, st, 4, rpp)
+                with StdoutToStderr():
+                    line["ref_gpu"] = ref_gpu_baseline(objs, st, 4, rpp)
             except Exception as ex:
                 line["ref_gpu"] = {"unavailable": repr(ex)}
         print(json.dumps(line), flush=True)

@@ -99,6 +99,7 @@ class BuildInfo(C.Structure):
     _fields_ = [
         ("nprims", C.c_int64), ("nnodes", C.c_int64), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3),
         ("upload_ms", C.c_float), ("build_ms", C.c_float), ("max_depth", C.c_int32), ("rebuild_iterations", C.c_int32),
+        ("nwide", C.c_int64), ("wide_levels", C.c_int32),
     ]
 
 
@@ -128,6 +129,7 @@ _sig("drb_settings_default", None, C.POINTER(Settings))
 _sig("drb_scene_create", _i, _vp, _i, _pp)
 _sig("drb_scene_create_ex", _i, _vp, _i, _u32, _pp)
 _sig("drb_scene_tree", _i, _vp, _vp, _vp, _vp, _vp)
+_sig("drb_scene_wide", _i, _vp, _vp, _vp)
 _sig("drb_scene_load", _i, _cp, _cp, _i, _pp)
 _sig("drb_scene_free", None, _vp)
 _sig("drb_scene_settings", _i, _vp, C.POINTER(Settings))
@@ -156,7 +158,7 @@ EXPORTED_SYMBOLS = [
     "drb_host_scene_load", "drb_host_scene_parse", "drb_host_scene_create", "drb_host_scene_free",
     "drb_host_scene_num_objects", "drb_host_scene_objects", "drb_host_scene_settings",
     "drb_host_scene_num_textures", "drb_host_scene_texture_path", "drb_host_scene_num_skipped",
-    "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_create_ex", "drb_scene_tree", "drb_scene_load", "drb_scene_free",
+    "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_create_ex", "drb_scene_tree", "drb_scene_wide", "drb_scene_load", "drb_scene_free",
     "drb_scene_settings", "drb_scene_num_prims", "drb_scene_num_objects", "drb_scene_build_info",
     "drb_scene_lbvh", "drb_opts_default", "drb_render_device", "drb_render", "drb_frame_i3",
     "drb_trace_ids", "drb_primary_rays", "drb_tonemap", "drb_tonemap_device", "drb_write_bmp",
@@ -351,6 +353,13 @@ class Scene:
         nmin = np.zeros((ni, 3), np.float32); nmax = np.zeros((ni, 3), np.float32)
         _check(_lib.drb_scene_tree(self._h, left.ctypes.data, right.ctypes.data, nmin.ctypes.data, nmax.ctypes.data))
         return dict(left=left, right=right, node_min=nmin, node_max=nmax)
+
+    def wide(self):
+        """The four-wide traversal nodes: child (n,4) int32 and boxes (n,4,3) uint32 (min_q | max_q << 16)."""
+        n = int(self.build_info.nwide)
+        child = np.zeros((n, 4), np.int32); boxes = np.zeros((n, 4, 3), np.uint32)
+        _check(_lib.drb_scene_wide(self._h, child.ctypes.data, boxes.ctypes.data))
+        return dict(child=child, boxes=boxes)
 
     @staticmethod
     def _opts(seed=0, sample_base=0, sample_count=0, batch_paths=0, flags=0, stream=None) -> Opts:

@@ -21,6 +21,18 @@ struct __align__(32) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 32, "BvhNode must be 32 bytes");
 
+// 64 B four-wide node, two 256-bit loads: the binary hierarchy collapsed two levels at a time (k_wide_* in
+// scene.cu).  Same 16-bit grid and outward rounding as BvhNode.
+//   bx[c], by[c], bz[c] = min_q | max_q << 16 of child c on each axis; an empty slot has min 65535 > max 0
+//   child[c] >= 0: wide node index, < 0: leaf, ~child = primitive slot, kWideEmpty: no child
+struct __align__(32) WideNode {
+    uint32_t bx[4], by[4];
+    uint32_t bz[4];
+    int32_t child[4];
+};
+static_assert(sizeof(WideNode) == 64, "WideNode must be 64 bytes");
+#define DRB_WIDE_EMPTY ((int32_t)0x80000000)
+
 // The quantisation grid of one axis: 65528 quanta span the scene bounds, 4 spare quanta on each side so the
 // outward margin never clamps.  Same single float operations on host and device.
 #ifdef __CUDACC__
@@ -106,6 +118,9 @@ struct drb_scene {
     int64_t nprims = 0;         // renderable primitives (in the tree)
     int64_t nnodes = 0;
     BvhNode* nodes = nullptr;
+    WideNode* wnodes = nullptr; // the traversal structure
+    int64_t nwnodes = 0;
+    int wide_levels = 0;        // height of the wide tree (levels of the breadth-first collapse)
     Prim* prims = nullptr;
     ShadeRec* recs = nullptr;
     int32_t* orig_id = nullptr; // prim slot -> object line index

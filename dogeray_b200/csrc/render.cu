@@ -38,6 +38,9 @@ constexpr int kTraceThreads = 128;
 #ifndef DRB_TRACE_STEPS
 #define DRB_TRACE_STEPS 2
 #endif
+#ifndef DRB_SORTED_PUSH
+#define DRB_SORTED_PUSH 0
+#endif
 constexpr int kSteps = DRB_TRACE_STEPS;   // descent steps per lane between two rounds of warp votes
 constexpr uint32_t kInvalidPid = 0xFFFFFFFFu;
 constexpr float kTMax = 10000.0f;       // singlehit's mindist / aabb2's t_max, kernel.cu:246, 435
@@ -63,7 +66,7 @@ struct FrameParams {
 
 struct DevScene {
     float qlo[3], qscale[3];            // quantisation grid of the node boxes (drb_quant_grid)
-    const BvhNode* nodes;
+    const WideNode* wnodes;
     const Prim* prims;
     const ShadeRec* recs;
     const DevTexture* textures;
@@ -287,25 +290,48 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, float scen
 #pragma unroll
         for (int step = 0; step < kSteps; ++step) {
         if (node >= 0) {
-            const f8 nd = ldg256(sc.nodes + node);                    // the whole node: one 256-bit load
-            const uint32_t w0 = __float_as_uint(nd.lo.x), w1 = __float_as_uint(nd.lo.y), w2 = __float_as_uint(nd.lo.z);
-            const uint32_t w3 = __float_as_uint(nd.lo.w), w4 = __float_as_uint(nd.hi.x), w5 = __float_as_uint(nd.hi.y);
-            const int2 link = make_int2(__float_as_int(nd.hi.z), __float_as_int(nd.hi.w));
-#define DRB_PLANE(w, sel, s_, c_) fmaf(prmt_exp23((w), (sel)), (s_), (c_))
-            const float tn0 = fmaxf(fmaxf(DRB_PLANE(w0, snx, sx, cnx), DRB_PLANE(w1, sny, sy, cny)), fmaxf(DRB_PLANE(w2, snz, sz, cnz), 0.0f));
-            const float tf0 = fminf(fminf(DRB_PLANE(w0, sfx, sx, cfx), DRB_PLANE(w1, sfy, sy, cfy)), fminf(DRB_PLANE(w2, sfz, sz, cfz), best));
-            const float tn1 = fmaxf(fmaxf(DRB_PLANE(w3, snx, sx, cnx), DRB_PLANE(w4, sny, sy, cny)), fmaxf(DRB_PLANE(w5, snz, sz, cnz), 0.0f));
-            const float tf1 = fminf(fminf(DRB_PLANE(w3, sfx, sx, cfx), DRB_PLANE(w4, sfy, sy, cfy)), fminf(DRB_PLANE(w5, sfz, sz, cfz), best));
+            const WideNode* np = sc.wnodes + node;
+            const f8 nA = ldg256(np->bx), nB = ldg256(np->bz);          // the whole node: two 256-bit loads
+#define DRB_PLANE(w, sel, s_, c_) fmaf(prmt_exp23(__float_as_uint(w), (sel)), (s_), (c_))
+#define DRB_CHILD(c, wx, wy, wz)                                                                                              \
+            const float tn##c = fmaxf(fmaxf(DRB_PLANE(wx, snx, sx, cnx), DRB_PLANE(wy, sny, sy, cny)), fmaxf(DRB_PLANE(wz, snz, sz, cnz), 0.0f)); \
+            const float tf##c = fminf(fminf(DRB_PLANE(wx, sfx, sx, cfx), DRB_PLANE(wy, sfy, sy, cfy)), fminf(DRB_PLANE(wz, sfz, sz, cfz), best)); \
+            const uint32_t k##c = (tn##c <= tf##c) ? ((__float_as_uint(tn##c) & 0xFFFFFFFCu) | c##u) : 0xFFFFFFFFu;
+            DRB_CHILD(0, nA.lo.x, nA.hi.x, nB.lo.x)
+            DRB_CHILD(1, nA.lo.y, nA.hi.y, nB.lo.y)
+            DRB_CHILD(2, nA.lo.z, nA.hi.z, nB.lo.z)
+            DRB_CHILD(3, nA.lo.w, nA.hi.w, nB.lo.w)
+#undef DRB_CHILD
 #undef DRB_PLANE
-            const bool h0 = tn0 <= tf0;
-            const bool h1 = tn1 <= tf1;
-            if (h0 && h1) {
-                const bool swap = tn1 < tn0;
-                DRB_PUSH(swap ? link.x : link.y);
-                node = swap ? link.y : link.x;
-            } else if (h0) node = link.x;
-            else if (h1) node = link.y;
-            else node = DRB_POP();
+            // t_near >= 0, so its bits order like unsigned integers; the two low bits carry the slot
+#if DRB_SORTED_PUSH
+            // sort the four keys (5 compare-exchanges), push the hits far-to-near, continue with the nearest
+            uint32_t a0 = min(k0, k1), a1 = max(k0, k1), a2 = min(k2, k3), a3 = max(k2, k3);
+            const uint32_t s0 = min(a0, a2), t1 = max(a0, a2), t2 = min(a1, a3), s3 = max(a1, a3);
+            const uint32_t s1 = min(t1, t2), s2 = max(t1, t2);
+            if (s0 == 0xFFFFFFFFu) node = DRB_POP();
+            else {
+                const int c0 = __float_as_int(nB.hi.x), c1 = __float_as_int(nB.hi.y), c2 = __float_as_int(nB.hi.z), c3 = __float_as_int(nB.hi.w);
+#define DRB_LINK(k) (((k) & 3u) == 0u ? c0 : (((k) & 3u) == 1u ? c1 : (((k) & 3u) == 2u ? c2 : c3)))
+                if (s3 != 0xFFFFFFFFu) DRB_PUSH(DRB_LINK(s3));
+                if (s2 != 0xFFFFFFFFu) DRB_PUSH(DRB_LINK(s2));
+                if (s1 != 0xFFFFFFFFu) DRB_PUSH(DRB_LINK(s1));
+                node = DRB_LINK(s0);
+#undef DRB_LINK
+            }
+#else
+            const uint32_t kmin = min(min(k0, k1), min(k2, k3));
+            if (kmin == 0xFFFFFFFFu) node = DRB_POP();
+            else {
+                const int c0 = __float_as_int(nB.hi.x), c1 = __float_as_int(nB.hi.y), c2 = __float_as_int(nB.hi.z), c3 = __float_as_int(nB.hi.w);
+                if (k3 != kmin && k3 != 0xFFFFFFFFu) DRB_PUSH(c3);
+                if (k2 != kmin && k2 != 0xFFFFFFFFu) DRB_PUSH(c2);
+                if (k1 != kmin && k1 != 0xFFFFFFFFu) DRB_PUSH(c1);
+                if (k0 != kmin && k0 != 0xFFFFFFFFu) DRB_PUSH(c0);
+                const uint32_t near = kmin & 3u;
+                node = near == 0u ? c0 : (near == 1u ? c1 : (near == 2u ? c2 : c3));
+            }
+#endif
         }
         // a lane that arrives at a leaf stashes it and keeps descending
         if (node < 0 && node != kSentinel && leaf == 0) { leaf = node; node = DRB_POP(); }
@@ -742,7 +768,8 @@ int ensure_buffers(drb_scene* s, size_t slots)
     rb->capacity = slots;
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    rb->trace_smem = (size_t)(std::max(s->info.max_depth, 1) + 2) * kTraceThreads * sizeof(int);
+    // worst case three pushes per level of the four-wide tree, plus the sentinel
+    rb->trace_smem = (size_t)(3 * std::max(s->wide_levels, 1) + 2) * kTraceThreads * sizeof(int);
     DRB_CUDA(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb->trace_smem));
     DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, kTraceThreads, rb->trace_smem));
     rb->trace_blocks = sms * std::max(per_sm, 1);
@@ -755,7 +782,7 @@ DevScene dev_scene(const drb_scene* s)
 {
     DevScene d;
     for (int a = 0; a < 3; ++a) drb_quant_grid(s->info.bounds_min[a], s->info.bounds_max[a], &d.qlo[a], &d.qscale[a]);
-    d.nodes = s->nodes; d.prims = s->prims; d.recs = s->recs; d.textures = s->textures;
+    d.wnodes = s->wnodes; d.prims = s->prims; d.recs = s->recs; d.textures = s->textures;
     d.nprims = (int)s->nprims; d.ntextures = s->ntextures;
     return d;
 }

@@ -384,6 +384,84 @@ __global__ void k_emit_relabelled(int n, const float4* __restrict__ lmin, const 
     fmin[dst] = node_min[i]; fmax[dst] = node_max[i];
 }
 
+// ---- collapse to four-wide nodes ------------------------------------------------------------------------
+// Breadth first over the final binary tree (root = node 0).  A wide node starts from a binary node's two
+// children and twice replaces the internal child of largest surface area by that child's own two children
+// (ties: lowest slot), giving up to four children.  Ids are assigned level by level from prefix sums, so the
+// result is deterministic and oracle/lbvh_host.c reproduces it bit for bit.
+__device__ __forceinline__ float box_half_area(const float4& lo, const float4& hi)
+{
+    const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return ex * ey + ey * ez + ez * ex;
+}
+
+__global__ void k_wide_expand(int nq, const int32_t* __restrict__ queue, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                              const float4* __restrict__ node_min, const float4* __restrict__ node_max, int4* __restrict__ slots, int* __restrict__ counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int b = queue[i];
+    int s[4] = { left[b], right[b], DRB_WIDE_EMPTY, DRB_WIDE_EMPTY };
+    int n = 2;
+    for (int it = 0; it < 2; ++it) {
+        int pick = -1; float best = -1.0f;
+        for (int k = 0; k < n; ++k)
+            if (s[k] >= 0) {
+                const float a = box_half_area(node_min[s[k]], node_max[s[k]]);
+                if (a > best) { best = a; pick = k; }
+            }
+        if (pick < 0) break;
+        const int c = s[pick];
+        s[pick] = left[c];
+        s[n++] = right[c];
+    }
+    int internal = 0;
+    for (int k = 0; k < 4; ++k) internal += (s[k] >= 0) ? 1 : 0;
+    slots[i] = make_int4(s[0], s[1], s[2], s[3]);
+    counts[i] = internal;
+}
+
+__global__ void k_wide_emit(int nq, int level_base, int next_base, const int4* __restrict__ slots, const int* __restrict__ counts,
+                            const int* __restrict__ offsets, const float4* __restrict__ lmin, const float4* __restrict__ lmax,
+                            const float4* __restrict__ node_min, const float4* __restrict__ node_max, const int* __restrict__ scene_bounds,
+                            WideNode* __restrict__ out, int32_t* __restrict__ next_queue, int* __restrict__ total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int4 s4 = slots[i];
+    const int s[4] = { s4.x, s4.y, s4.z, s4.w };
+    const int off = offsets[i];
+    if (i == nq - 1) *total = off + counts[i];
+    WideNode nd;
+    int j = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t q[3] = { 0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu };          // min 65535 > max 0: never hit
+        int link = DRB_WIDE_EMPTY;
+        if (s[k] != DRB_WIDE_EMPTY) {
+            if (s[k] < 0) { quant_child(lmin[~s[k]], lmax[~s[k]], scene_bounds, q); link = s[k]; }
+            else {
+                quant_child(node_min[s[k]], node_max[s[k]], scene_bounds, q);
+                link = next_base + off + j;
+                next_queue[off + j] = s[k];
+                ++j;
+            }
+        }
+        nd.bx[k] = q[0]; nd.by[k] = q[1]; nd.bz[k] = q[2]; nd.child[k] = link;
+    }
+    out[level_base + i] = nd;
+}
+
+__global__ void k_wide_single(const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int* __restrict__ scene_bounds, WideNode* __restrict__ out)
+{
+    WideNode nd;
+    uint32_t q[3];
+    quant_child(lmin[0], lmax[0], scene_bounds, q);
+    for (int k = 0; k < 4; ++k) { nd.bx[k] = nd.by[k] = nd.bz[k] = 0x0000FFFFu; nd.child[k] = DRB_WIDE_EMPTY; }
+    nd.bx[0] = q[0]; nd.by[0] = q[1]; nd.bz[0] = q[2]; nd.child[0] = ~0;
+    out[0] = nd;
+}
+
 __global__ void k_emit_nodes(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
                              const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
                              const int* __restrict__ scene_bounds, BvhNode* __restrict__ nodes)
@@ -649,6 +727,40 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
             k_emit_single<<<1, 1, 0, st>>>(lmin, lmax, d_bounds, s->nodes);
             height = 1;
         }
+        // ---- four-wide collapse of the final tree (s->tree.*, root 0)
+        if (int rc = dev_alloc(&s->wnodes, nint, st)) return rc;
+        if (nprims > 1) {
+            int32_t* wq[2]; int4* wslots; int *wcounts, *woffs, *wtotal;
+            if (int rc = tmp.alloc(&wq[0], (size_t)nprims)) return rc;
+            if (int rc = tmp.alloc(&wq[1], (size_t)nprims)) return rc;
+            if (int rc = tmp.alloc(&wslots, (size_t)nprims)) return rc;
+            if (int rc = tmp.alloc(&wcounts, (size_t)nprims)) return rc;
+            if (int rc = tmp.alloc(&woffs, (size_t)nprims)) return rc;
+            if (int rc = tmp.alloc(&wtotal, 1)) return rc;
+            size_t wscan_bytes = 0;
+            DRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, wscan_bytes, wcounts, woffs, nprims, st));
+            void* d_wscan = nullptr;
+            if (int rc = tmp.alloc((char**)&d_wscan, wscan_bytes)) return rc;
+            DRB_CUDA(cudaMemsetAsync(wq[0], 0, sizeof(int32_t), st));        // level 0 = { binary root 0 }
+            int nq = 1, level_base = 0, cur = 0, levels = 0;
+            while (nq > 0) {
+                const int g = (nq + T - 1) / T;
+                k_wide_expand<<<g, T, 0, st>>>(nq, wq[cur], s->tree.left, s->tree.right, s->tree.node_min, s->tree.node_max, wslots, wcounts);
+                DRB_CUDA(cub::DeviceScan::ExclusiveSum(d_wscan, wscan_bytes, wcounts, woffs, nq, st));
+                k_wide_emit<<<g, T, 0, st>>>(nq, level_base, level_base + nq, wslots, wcounts, woffs, lmin, lmax, s->tree.node_min, s->tree.node_max,
+                                             d_bounds, s->wnodes, wq[cur ^ 1], wtotal);
+                int tot = 0;
+                DRB_CUDA(cudaMemcpyAsync(&tot, wtotal, sizeof tot, cudaMemcpyDeviceToHost, st));
+                DRB_CUDA(cudaStreamSynchronize(st));
+                level_base += nq; nq = tot; cur ^= 1; ++levels;
+                if (levels > 4096 || level_base + nq > (int)nint) { drb_set_error("wide collapse overran (%d nodes, level %d)", level_base + nq, levels); return DRB_ERR_CUDA; }
+            }
+            s->nwnodes = level_base; s->wide_levels = levels;
+        } else {
+            k_wide_single<<<1, 1, 0, st>>>(lmin, lmax, d_bounds, s->wnodes);
+            s->nwnodes = 1; s->wide_levels = 1;
+        }
+        s->info.nwide = s->nwnodes; s->info.wide_levels = s->wide_levels;
         int hb[6];
         DRB_CUDA(cudaMemcpyAsync(hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
         DRB_CUDA(cudaEventRecord(e2, st));
@@ -727,7 +839,7 @@ void drb_scene_free(drb_scene* s)
     if (st) cudaStreamSynchronize(st);
     for (void* p : { (void*)s->nodes, (void*)s->prims, (void*)s->recs, (void*)s->orig_id, (void*)s->textures, (void*)s->dbg.keys,
                      (void*)s->dbg.order, (void*)s->dbg.parent, (void*)s->dbg.left, (void*)s->dbg.right, (void*)s->dbg.node_min,
-                     (void*)s->dbg.node_max, (void*)s->tree.left, (void*)s->tree.right, (void*)s->tree.node_min, (void*)s->tree.node_max })
+                     (void*)s->dbg.node_max, (void*)s->tree.left, (void*)s->tree.right, (void*)s->tree.node_min, (void*)s->tree.node_max, (void*)s->wnodes })
         if (p) drb_dev_free(p, st);
     for (void* p : s->texture_storage) drb_dev_free(p, st);
     if (st) cudaStreamDestroy(st);
@@ -816,6 +928,22 @@ int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* 
             for (size_t i = 0; i < ni; ++i) { node_max[3*i] = tmp[i].x; node_max[3*i+1] = tmp[i].y; node_max[3*i+2] = tmp[i].z; }
         }
     }
+    return DRB_OK;
+}
+
+int drb_scene_wide(const drb_scene* s, int32_t* child, uint32_t* boxes)
+{
+    if (!s) { drb_set_error("drb_scene_wide: null scene"); return DRB_ERR_ARG; }
+    DRB_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->nwnodes;
+    if (!n) return DRB_OK;
+    std::vector<WideNode> tmp(n);
+    DRB_CUDA(cudaMemcpy(tmp.data(), s->wnodes, n * sizeof(WideNode), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 4; ++k) {
+            if (child) child[4 * i + k] = tmp[i].child[k];
+            if (boxes) { boxes[12 * i + 3 * k] = tmp[i].bx[k]; boxes[12 * i + 3 * k + 1] = tmp[i].by[k]; boxes[12 * i + 3 * k + 2] = tmp[i].bz[k]; }
+        }
     return DRB_OK;
 }
 

@@ -129,6 +129,8 @@ typedef struct drb_build_info {
     float upload_ms, build_ms;
     int32_t max_depth;          /* height of the traversal tree */
     int32_t rebuild_iterations; /* clustering rounds of the SAH-guided rebuild (0 with DRB_BUILD_LBVH_ONLY) */
+    int64_t nwide;              /* four-wide traversal nodes */
+    int32_t wide_levels;        /* height of the four-wide tree */
 } drb_build_info;
 int drb_scene_build_info(const drb_scene* s, drb_build_info* out);
 
@@ -143,6 +145,11 @@ int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* 
 /* The hierarchy the traversal nodes were emitted from, root = node 0, same child encoding as
  * drb_scene_lbvh; equals the Karras tree with DRB_BUILD_LBVH_ONLY.  For the bit-exact host check. */
 int drb_scene_tree(const drb_scene* s, int32_t* left, int32_t* right, float* node_min, float* node_max);
+
+/* The four-wide traversal nodes (collapsed from drb_scene_tree's hierarchy): child[4*i + k] is child k of node i
+ * (>= 0 wide node, < 0 leaf ~primitive slot, INT32_MIN empty); boxes[12*i + 3*k + a] is min_q | max_q << 16 of
+ * that child on axis a (16-bit scene grid).  nwide entries each (drb_build_info.nwide). */
+int drb_scene_wide(const drb_scene* s, int32_t* child, uint32_t* boxes);
 
 /* ---- rendering ------------------------------------------------------------------------ */
 typedef struct drb_opts {

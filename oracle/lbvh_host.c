@@ -203,3 +203,84 @@ int ploc_host_build(const float* lmin, const float* lmax, int n, int radius, int
     free(nn); free(pl); free(pr); free(pmin); free(pmax);
     return height;
 }
+
+/* ---- host mirror of the four-wide collapse (k_wide_* in dogeray_b200/csrc/scene.cu) ---------------------
+ * Input: the final binary tree (root 0; left/right with leaves as ~sorted_position; node boxes; sorted leaf
+ * boxes) and the scene bounds.  Output: child[4*i + k], boxes[12*i + 3*k + a] (min_q | max_q << 16 on the
+ * 16-bit scene grid), breadth-first ids.  Returns the number of wide nodes; *levels gets the tree height. */
+static float box_half_area3(const float* lo, const float* hi)
+{
+    float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    return ex * ey + ey * ez + ez * ex;
+}
+static uint32_t quant_axis_h(float lo, float hi, float qlo, float qscale)
+{
+    int a = (int)floorf((lo - qlo) / qscale) - 1;
+    int b = (int)ceilf((hi - qlo) / qscale) + 1;
+    if (a < 0) a = 0;
+    if (a > 65535) a = 65535;
+    if (b < 0) b = 0;
+    if (b > 65535) b = 65535;
+    return (uint32_t)a | ((uint32_t)b << 16);
+}
+#define WIDE_EMPTY ((int32_t)0x80000000)
+
+int wide_host_build(const int32_t* left, const int32_t* right, const float* node_min, const float* node_max, const float* lmin,
+                    const float* lmax, int n, const float* scene_bounds, int32_t* child, uint32_t* boxes, int* levels)
+{
+    float qlo[3], qs[3];
+    for (int a = 0; a < 3; a++) {
+        float ext = scene_bounds[3 + a] - scene_bounds[a];
+        if (!(ext > 0.0f)) ext = 1.0f;
+        qs[a] = ext / 65527.0f;
+        qlo[a] = scene_bounds[a] - 4.0f * qs[a];
+    }
+    if (n == 1) {
+        for (int k = 0; k < 4; k++) { child[k] = WIDE_EMPTY; for (int a = 0; a < 3; a++) boxes[3 * k + a] = 0x0000FFFFu; }
+        child[0] = ~0;
+        for (int a = 0; a < 3; a++) boxes[a] = quant_axis_h(lmin[a], lmax[a], qlo[a], qs[a]);
+        *levels = 1;
+        return 1;
+    }
+    int32_t* q[2]; q[0] = malloc(4 * (size_t)n); q[1] = malloc(4 * (size_t)n);
+    q[0][0] = 0;
+    int nq = 1, base = 0, cur = 0, lev = 0;
+    while (nq > 0) {
+        int next = 0, next_base = base + nq;
+        for (int i = 0; i < nq; i++) {
+            int b = q[cur][i];
+            int s[4] = { left[b], right[b], WIDE_EMPTY, WIDE_EMPTY };
+            int cnt = 2;
+            for (int it = 0; it < 2; it++) {
+                int pick = -1; float best = -1.0f;
+                for (int k = 0; k < cnt; k++)
+                    if (s[k] >= 0) {
+                        float ar = box_half_area3(node_min + 3 * (size_t)s[k], node_max + 3 * (size_t)s[k]);
+                        if (ar > best) { best = ar; pick = k; }
+                    }
+                if (pick < 0) break;
+                int c = s[pick];
+                s[pick] = left[c];
+                s[cnt++] = right[c];
+            }
+            int id = base + i;
+            for (int k = 0; k < 4; k++) {
+                int link = WIDE_EMPTY;
+                uint32_t qq[3] = { 0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu };
+                if (s[k] != WIDE_EMPTY) {
+                    const float* lo = s[k] < 0 ? lmin + 3 * (size_t)(~s[k]) : node_min + 3 * (size_t)s[k];
+                    const float* hi = s[k] < 0 ? lmax + 3 * (size_t)(~s[k]) : node_max + 3 * (size_t)s[k];
+                    for (int a = 0; a < 3; a++) qq[a] = quant_axis_h(lo[a], hi[a], qlo[a], qs[a]);
+                    if (s[k] < 0) link = s[k];
+                    else { link = next_base + next; q[cur ^ 1][next++] = s[k]; }
+                }
+                child[4 * (size_t)id + k] = link;
+                for (int a = 0; a < 3; a++) boxes[12 * (size_t)id + 3 * k + a] = qq[a];
+            }
+        }
+        base = next_base; nq = next; cur ^= 1; lev++;
+    }
+    free(q[0]); free(q[1]);
+    *levels = lev;
+    return base;
+}

@@ -36,6 +36,8 @@ def _load():
     L.lbvh_host_build.restype = C.c_int
     L.ploc_host_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
     L.ploc_host_build.restype = C.c_int
+    L.wide_host_build.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 4
+    L.wide_host_build.restype = C.c_int
     return L
 
 
@@ -133,3 +135,18 @@ def ploc_host(lmin_sorted: np.ndarray, lmax_sorted: np.ndarray, radius: int = 16
     nmin = np.zeros((ni, 3), np.float32); nmax = np.zeros((ni, 3), np.float32)
     h = L.ploc_host_build(lmin.ctypes.data, lmax.ctypes.data, n, radius, left.ctypes.data, right.ctypes.data, nmin.ctypes.data, nmax.ctypes.data)
     return dict(left=left, right=right, node_min=nmin, node_max=nmax, height=h)
+
+
+def wide_host(left, right, node_min, node_max, lmin_sorted, lmax_sorted, scene_bounds):
+    """Host mirror of the four-wide collapse: dict(child (n,4), boxes (n,4,3), levels)."""
+    L = _load()
+    left = np.ascontiguousarray(left, np.int32); right = np.ascontiguousarray(right, np.int32)
+    nmin = np.ascontiguousarray(node_min, np.float32); nmax = np.ascontiguousarray(node_max, np.float32)
+    lmin = np.ascontiguousarray(lmin_sorted, np.float32); lmax = np.ascontiguousarray(lmax_sorted, np.float32)
+    sb = np.ascontiguousarray(scene_bounds, np.float32)
+    n = len(lmin)
+    child = np.zeros((max(n - 1, 1), 4), np.int32); boxes = np.zeros((max(n - 1, 1), 4, 3), np.uint32)
+    lev = C.c_int(0)
+    nw = L.wide_host_build(left.ctypes.data, right.ctypes.data, nmin.ctypes.data, nmax.ctypes.data, lmin.ctypes.data, lmax.ctypes.data, n,
+                           sb.ctypes.data, child.ctypes.data, boxes.ctypes.data, C.byref(lev))
+    return dict(child=child[:nw], boxes=boxes[:nw], levels=lev.value)

@@ -244,6 +244,11 @@ def test_gpu_lbvh_bit_exact_against_host_build():
             assert np.array_equal(dt["left"], ph["left"]) and np.array_equal(dt["right"], ph["right"])
             assert np.array_equal(dt["node_min"], ph["node_min"]) and np.array_equal(dt["node_max"], ph["node_max"])
             assert bi.max_depth == ph["height"] and bi.rebuild_iterations > 0
+            # ... and the four-wide collapse of that tree (ids, links, 16-bit boxes)
+            wh = restated.wide_host(ph["left"], ph["right"], ph["node_min"], ph["node_max"], lmin, lmax, host["scene_bounds"])
+            dw = sc.wide()
+            assert bi.nwide == len(wh["child"]) and bi.wide_levels == wh["levels"]
+            assert np.array_equal(dw["child"], wh["child"]) and np.array_equal(dw["boxes"], wh["boxes"])
             lb = drb.Scene.from_host(drb.HostScene.from_objects(objs), build_flags=drb.BUILD_LBVH_ONLY)
             assert lb.build_info.max_depth == host["height"] and lb.build_info.rebuild_iterations == 0
             lt = lb.tree()

@@ -133,3 +133,22 @@ def test_host_lbvh_is_a_valid_tree():
                     assert ch > k
                     stack.append(int(ch))
         assert (seen == 1).all() and np.array_equal(p["node_min"][0], (c - e).min(0))
+        # four-wide collapse: every leaf once, quantised child boxes contain the float boxes they came from
+        sb = np.concatenate([(c - e).min(0), (c + e).max(0)])
+        w = restated.wide_host(p["left"], p["right"], p["node_min"], p["node_max"], lmin, lmax, sb)
+        qs = np.where(sb[3:] - sb[:3] > 0, sb[3:] - sb[:3], 1).astype(np.float32) / np.float32(65527.0)
+        qlo = sb[:3] - np.float32(4.0) * qs
+        seen = np.zeros(n, int)
+        for i in range(len(w["child"])):
+            for k in range(4):
+                ch = w["child"][i, k]
+                if ch == -2 ** 31:
+                    assert (w["boxes"][i, k] == 0xFFFF).all()
+                    continue
+                lo_q = (w["boxes"][i, k] & 0xFFFF).astype(np.float64); hi_q = (w["boxes"][i, k] >> 16).astype(np.float64)
+                if ch < 0:
+                    seen[~ch] += 1
+                    assert (qlo + lo_q * qs <= lmin[~ch]).all() and (qlo + hi_q * qs >= lmax[~ch]).all()
+                else:
+                    assert i < ch < len(w["child"])
+        assert (seen == 1).all()
