@@ -1,6 +1,11 @@
 // dogeray-b200: headless drop-in for `raygpu.exe [scene.rts]` (raygpu/kernel.cu:2021-2051, 2486-2516).
 //
 //   dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]
+//                [--snapshot-every N] [--save-acc file.acc] [--resume file.acc]
+//
+// --snapshot-every N renders N samples per pixel at a time and rewrites the image after every chunk (the headless
+// stand-in for the window's progressive accumulate loop, kernel.cu:2154-2224); --save-acc / --resume checkpoint the
+// float accumulator and its sample count, so a render can be continued later with the next sample indices.
 //
 // Like the reference it opens `scene.rts` when no path is given, looks for textures among the *.ppm files of the
 // current working directory, and writes `<scene path>.bmp` (the file SPACE exports, 32-bpp V4 header).  Unlike the
@@ -22,7 +27,8 @@ static int fail(const char* what)
 int main(int argc, char** argv)
 {
     std::string scene_path = "scene.rts", out_path;
-    int spp = -1, depth = -1, w = -1, h = -1, device = 0;
+    std::string save_acc, resume_acc;
+    int spp = -1, depth = -1, w = -1, h = -1, device = 0, snapshot_every = 0;
     unsigned long long seed = 0;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -35,9 +41,13 @@ int main(int argc, char** argv)
         else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
         else if (a == "--device") device = atoi(next("--device"));
         else if (a == "--out") out_path = next("--out");
+        else if (a == "--snapshot-every") snapshot_every = atoi(next("--snapshot-every"));
+        else if (a == "--save-acc") save_acc = next("--save-acc");
+        else if (a == "--resume") resume_acc = next("--resume");
         else if (a == "--res") { if (sscanf(next("--res"), "%dx%d", &w, &h) != 2) { fprintf(stderr, "dogeray-b200: --res wants WxH\n"); return 2; } }
         else if (a == "-h" || a == "--help") {
-            printf("usage: dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]\n");
+            printf("usage: dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]\n"
+                   "                    [--snapshot-every N] [--save-acc file.acc] [--resume file.acc]\n");
             return 0;
         } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "dogeray-b200: unknown option %s\n", a.c_str()); return 2; }
         else scene_path = a;
@@ -61,17 +71,57 @@ int main(int argc, char** argv)
     drb_opts opts;
     drb_opts_default(&opts);
     opts.seed = seed;
-    std::vector<float> accum((size_t)st.width * st.height * 3);
-    drb_stats stats;
-    if (drb_render(scene, &st, &opts, accum.data(), &stats) != DRB_OK) return fail("render failed");
-    printf("Time = %.3f ms  %llu samples  %.1f Mrays/s\n", stats.total_ms, (unsigned long long)st.spp,
-           stats.total_ms > 0 ? stats.rays / (stats.total_ms * 1e-3) / 1e6 : 0.0);
-    std::vector<uint8_t> rgb(accum.size());
-    if (drb_tonemap(accum.data(), st.width, st.height, st.spp > 0 ? st.spp : 1, rgb.data()) != DRB_OK) return fail("tonemap failed");
+    std::vector<float> accum((size_t)st.width * st.height * 3, 0.0f);
+    // checkpoint header: magic, width, height, samples accumulated so far, seed
+    struct AccHeader { char magic[8]; int32_t w, h; uint64_t samples, seed; };
+    uint64_t have = 0;
+    if (!resume_acc.empty()) {
+        FILE* f = fopen(resume_acc.c_str(), "rb");
+        AccHeader hd;
+        if (!f || fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "DRBACC1", 8) != 0 || hd.w != st.width || hd.h != st.height ||
+            fread(accum.data(), sizeof(float), accum.size(), f) != accum.size()) {
+            fprintf(stderr, "dogeray-b200: cannot resume from %s (missing, truncated, or another image size)\n", resume_acc.c_str());
+            return 1;
+        }
+        fclose(f);
+        have = hd.samples; seed = hd.seed;
+        printf("resumed %llu samples from %s\n", (unsigned long long)have, resume_acc.c_str());
+    }
     if (out_path.empty()) out_path = scene_path + ".bmp";
     const bool ppm = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".ppm";
-    int rc = ppm ? drb_write_ppm(out_path.c_str(), rgb.data(), st.width, st.height) : drb_write_bmp(out_path.c_str(), rgb.data(), st.width, st.height);
-    if (rc != DRB_OK) return fail("cannot write image");
+    std::vector<uint8_t> rgb(accum.size());
+    auto write_image = [&](uint64_t nsamples) -> int {
+        if (drb_tonemap(accum.data(), st.width, st.height, (double)(nsamples ? nsamples : 1), rgb.data()) != DRB_OK) return DRB_ERR_ARG;
+        return ppm ? drb_write_ppm(out_path.c_str(), rgb.data(), st.width, st.height) : drb_write_bmp(out_path.c_str(), rgb.data(), st.width, st.height);
+    };
+    const uint32_t total = (uint32_t)(st.spp > 0 ? st.spp : 0);
+    const uint32_t chunk = snapshot_every > 0 ? (uint32_t)snapshot_every : (total ? total : 1);
+    double ms_total = 0; uint64_t rays_total = 0;
+    for (uint32_t done = 0; done < total; done += chunk) {
+        drb_opts opts;
+        drb_opts_default(&opts);
+        opts.seed = seed;
+        opts.sample_base = (uint32_t)have;
+        opts.sample_count = total - done < chunk ? total - done : chunk;
+        opts.flags = DRB_FLAG_ACCUMULATE;
+        drb_stats stats;
+        if (drb_render(scene, &st, &opts, accum.data(), &stats) != DRB_OK) return fail("render failed");
+        have += opts.sample_count; ms_total += stats.total_ms; rays_total += stats.rays;
+        if (write_image(have) != DRB_OK) return fail("cannot write image");
+        if (snapshot_every > 0) printf("%llu samples -> %s\n", (unsigned long long)have, out_path.c_str());
+    }
+    if (total == 0 && write_image(have) != DRB_OK) return fail("cannot write image");
+    printf("Time = %.3f ms  %llu samples  %.1f Mrays/s\n", ms_total, (unsigned long long)have, ms_total > 0 ? rays_total / (ms_total * 1e-3) / 1e6 : 0.0);
+    if (!save_acc.empty()) {
+        AccHeader hd;
+        memset(&hd, 0, sizeof hd);
+        memcpy(hd.magic, "DRBACC1", 8); hd.w = st.width; hd.h = st.height; hd.samples = have; hd.seed = seed;
+        FILE* f = fopen(save_acc.c_str(), "wb");
+        if (!f || fwrite(&hd, sizeof hd, 1, f) != 1 || fwrite(accum.data(), sizeof(float), accum.size(), f) != accum.size() || fclose(f) != 0) {
+            fprintf(stderr, "dogeray-b200: cannot write %s\n", save_acc.c_str());
+            return 1;
+        }
+    }
     printf("exported image:%s\n", out_path.c_str());
     drb_scene_free(scene);
     drb_host_scene_free(hs);

@@ -218,7 +218,10 @@ constexpr int kSentinel = (int)0x80000000;     // bottom of every traversal stac
 // the idle lanes claim fresh rays from the queue with ONE atomic per warp (ballot + popc + shfl), so warps
 // stay populated until the queue runs dry.  (A while-while variant measured slower on B200: with
 // one-primitive leaves, lanes that reach a leaf wait for the slowest descent.)
-__global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, float scene_scale, Queues q, int cur, int refill, int leaf_batch, int step_min,
+#ifndef DRB_TRACE_MIN_BLOCKS
+#define DRB_TRACE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(DevScene sc, float scene_scale, Queues q, int cur, int refill, int leaf_batch, int step_min,
                                                const uint32_t* __restrict__ order)
 {
     const uint32_t count = q.counters[cur];

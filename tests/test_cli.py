@@ -54,3 +54,19 @@ def test_cli_renders_the_same_image_as_the_library(tmp_path):
     assert np.array_equal(px, drb.tonemap(acc, 3))
     p = subprocess.run([CLI, "scene.rts", "--spp", "1", "--res", "32x16", "--out", "o.ppm"], capture_output=True, text=True, cwd=tmp_path)
     assert p.returncode == 0 and open(tmp_path / "o.ppm", "rb").read().startswith(b"P6\n32 16\n255\n")
+
+
+@pytest.mark.gpu
+def test_cli_progressive_snapshots_and_resume(tmp_path):
+    """chunked accumulation + checkpoint/resume reproduce the one-shot image (disjoint Philox sample indices)"""
+    objs, st = synth.heightfield_scene(n=12, width=48, height=32, spp=6, max_depth=4)
+    drb.write_rts(str(tmp_path / "s.rts"), st, objs)
+    run = lambda *a: subprocess.run([CLI, "s.rts", "--seed", "4"] + list(a), capture_output=True, text=True, cwd=tmp_path)
+    p = run("--out", "full.ppm"); assert p.returncode == 0, p.stderr
+    p = run("--out", "prog.ppm", "--snapshot-every", "2"); assert p.returncode == 0 and p.stdout.count("samples -> prog.ppm") == 3
+    p = run("--spp", "4", "--out", "a.ppm", "--save-acc", "ck.acc"); assert p.returncode == 0
+    p = run("--spp", "2", "--out", "b.ppm", "--resume", "ck.acc"); assert p.returncode == 0 and "resumed 4 samples" in p.stdout
+    full = np.frombuffer(open(tmp_path / "full.ppm", "rb").read()[len(b"P6\n48 32\n255\n"):], np.uint8).astype(int)
+    for name in ("prog.ppm", "b.ppm"):
+        img = np.frombuffer(open(tmp_path / name, "rb").read()[len(b"P6\n48 32\n255\n"):], np.uint8).astype(int)
+        assert np.abs(img - full).max() <= 1                      # float sums in another association: at most one 8-bit step
