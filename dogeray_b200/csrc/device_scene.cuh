@@ -8,21 +8,11 @@
 #include <string>
 #include <vector>
 
-// 32 B binary node holding BOTH child boxes, fetched with ONE 256-bit load.
-// Child boxes are quantised to 16 bits per plane on a scene-wide grid (drb_quant_grid), rounded outwards
-// plus one quantum of margin, so a quantised box always contains the float box it came from:
-//   c0[a] = min_q | max_q << 16 for axis a of child 0, c1[a] likewise for child 1
-//   link[k] = child k: >= 0 node index, < 0 leaf, ~link = primitive slot
-// Traversal never converts the integers: PRMT drops a 16-bit half under the exponent 0x4B00 (the float
-// 2^23 + q) and one FMA with per-ray constants turns it into the plane's ray parameter.
-struct __align__(32) BvhNode {
-    uint32_t c0[3], c1[3];
-    int32_t link[2];
-};
-static_assert(sizeof(BvhNode) == 32, "BvhNode must be 32 bytes");
-
 // 64 B four-wide node, two 256-bit loads: the binary hierarchy collapsed two levels at a time (k_wide_* in
-// scene.cu).  Same 16-bit grid and outward rounding as BvhNode.
+// scene.cu).  Child boxes are quantised to 16 bits per plane on a scene-wide grid (drb_quant_grid), rounded outwards
+// plus one quantum of margin, so a quantised box always contains the float box it came from.  Traversal never
+// converts the integers: PRMT drops a 16-bit half under the exponent byte 0x4B (the float 2^23 + q) and one FMA with
+// per-ray constants turns it into the plane's ray parameter.
 //   bx[c], by[c], bz[c] = min_q | max_q << 16 of child c on each axis; an empty slot has min 65535 > max 0
 //   child[c] >= 0: wide node index, < 0: leaf, ~child = primitive slot, kWideEmpty: no child
 struct __align__(32) WideNode {
@@ -117,7 +107,6 @@ struct drb_scene {
     int64_t nobjects = 0;       // object lines
     int64_t nprims = 0;         // renderable primitives (in the tree)
     int64_t nnodes = 0;
-    BvhNode* nodes = nullptr;
     WideNode* wnodes = nullptr; // the traversal structure
     int64_t nwnodes = 0;
     int wide_levels = 0;        // height of the wide tree (levels of the breadth-first collapse)

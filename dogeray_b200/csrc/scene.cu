@@ -363,23 +363,16 @@ __device__ __forceinline__ void quant_child(const float4& lo, const float4& hi, 
 }
 
 // final labelling: node created k-th becomes (n - 2) - k, so the root is node 0 and parents precede children
-__global__ void k_emit_relabelled(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
+__global__ void k_relabel(int n, const int32_t* __restrict__ left,
                                   const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
-                                  const int* __restrict__ scene_bounds, BvhNode* __restrict__ nodes, int32_t* __restrict__ fleft,
-                                  int32_t* __restrict__ fright, float4* __restrict__ fmin, float4* __restrict__ fmax)
+                                  int32_t* __restrict__ fleft, int32_t* __restrict__ fright, float4* __restrict__ fmin,
+                                  float4* __restrict__ fmax)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     const int lc = left[i], rc = right[i];
-    const float4 a0 = lc < 0 ? lmin[~lc] : node_min[lc], a1 = lc < 0 ? lmax[~lc] : node_max[lc];
-    const float4 b0 = rc < 0 ? lmin[~rc] : node_min[rc], b1 = rc < 0 ? lmax[~rc] : node_max[rc];
     const int dst = (n - 2) - i;
     const int flc = lc < 0 ? lc : (n - 2) - lc, frc = rc < 0 ? rc : (n - 2) - rc;
-    BvhNode nd;
-    quant_child(a0, a1, scene_bounds, nd.c0);
-    quant_child(b0, b1, scene_bounds, nd.c1);
-    nd.link[0] = flc; nd.link[1] = frc;
-    nodes[dst] = nd;
     fleft[dst] = flc; fright[dst] = frc;
     fmin[dst] = node_min[i]; fmax[dst] = node_max[i];
 }
@@ -462,37 +455,6 @@ __global__ void k_wide_single(const float4* __restrict__ lmin, const float4* __r
     out[0] = nd;
 }
 
-__global__ void k_emit_nodes(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int32_t* __restrict__ left,
-                             const int32_t* __restrict__ right, const float4* __restrict__ node_min, const float4* __restrict__ node_max,
-                             const int* __restrict__ scene_bounds, BvhNode* __restrict__ nodes)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const int lc = left[i], rc = right[i];
-    const float4 a0 = lc < 0 ? lmin[~lc] : node_min[lc], a1 = lc < 0 ? lmax[~lc] : node_max[lc];
-    const float4 b0 = rc < 0 ? lmin[~rc] : node_min[rc], b1 = rc < 0 ? lmax[~rc] : node_max[rc];
-    BvhNode nd;
-    quant_child(a0, a1, scene_bounds, nd.c0);
-    quant_child(b0, b1, scene_bounds, nd.c1);
-    nd.link[0] = lc; nd.link[1] = rc;
-    nodes[i] = nd;
-}
-
-// a tree of one primitive: child0 = the leaf, child1 = an empty box
-__global__ void k_emit_single(const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int* __restrict__ scene_bounds,
-                              BvhNode* __restrict__ nodes)
-{
-    BvhNode nd;
-    quant_child(lmin[0], lmax[0], scene_bounds, nd.c0);
-    nd.c1[0] = nd.c1[1] = nd.c1[2] = 0x0000FFFFu;        // min 65535 > max 0: never hit
-    nd.link[0] = ~0; nd.link[1] = ~0;
-    nodes[0] = nd;
-}
-
-// All device memory comes from the device's default stream-ordered pool with its release threshold
-// raised to "never": a scene that is created, rendered and freed every frame (the reference's
-// CudaStarter pattern, kernel.cu:2604-2665) then recycles the same blocks instead of paying
-// cudaMalloc/cudaFree (hundreds of ms per frame for the ~3 GB a 1 M-triangle 1080p frame uses).
 template <typename T> int dev_alloc(T** p, size_t count, cudaStream_t st)
 {
     *p = nullptr;
@@ -622,7 +584,6 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
     if (int rc = dev_alloc(&s->prims, (size_t)nprims, st)) return rc;
     if (int rc = dev_alloc(&s->recs, (size_t)nprims, st)) return rc;
     if (int rc = dev_alloc(&s->orig_id, (size_t)nprims, st)) return rc;
-    if (int rc = dev_alloc(&s->nodes, (size_t)s->nnodes, st)) return rc;
     const size_t nint = nprims > 1 ? (size_t)nprims - 1 : 1;
     if (int rc = dev_alloc(&s->dbg.keys, (size_t)nprims, st)) return rc;
     if (int rc = dev_alloc(&s->dbg.order, (size_t)nprims, st)) return rc;
@@ -673,7 +634,6 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
             k_refit<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent, visits,
                                                        s->dbg.node_min, s->dbg.node_max, d_height);
             if (s->build_flags & DRB_BUILD_LBVH_ONLY) {
-                k_emit_nodes<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.node_min, s->dbg.node_max, d_bounds, s->nodes);
                 DRB_CUDA(cudaMemcpyAsync(s->tree.left, s->dbg.left, nint * 4, cudaMemcpyDeviceToDevice, st));
                 DRB_CUDA(cudaMemcpyAsync(s->tree.right, s->dbg.right, nint * 4, cudaMemcpyDeviceToDevice, st));
                 DRB_CUDA(cudaMemcpyAsync(s->tree.node_min, s->dbg.node_min, nint * 16, cudaMemcpyDeviceToDevice, st));
@@ -716,7 +676,7 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
                     node_base += tot[1]; n = tot[0]; cur ^= 1;
                 }
                 s->info.rebuild_iterations = iters;
-                k_emit_relabelled<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, pl, pr, pmin, pmax, d_bounds, s->nodes, s->tree.left, s->tree.right,
+                k_relabel<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, pl, pr, pmin, pmax, s->tree.left, s->tree.right,
                                                                           s->tree.node_min, s->tree.node_max);
                 float4 rootbox;
                 DRB_CUDA(cudaMemcpyAsync(&rootbox, pmin + (nprims - 2), sizeof rootbox, cudaMemcpyDeviceToHost, st));
@@ -724,7 +684,6 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
                 memcpy(&height, &rootbox.w, 4);
             }
         } else {
-            k_emit_single<<<1, 1, 0, st>>>(lmin, lmax, d_bounds, s->nodes);
             height = 1;
         }
         // ---- four-wide collapse of the final tree (s->tree.*, root 0)
@@ -837,7 +796,7 @@ void drb_scene_free(drb_scene* s)
     drb_render_buffers_free(s);
     cudaStream_t st = s->stream;
     if (st) cudaStreamSynchronize(st);
-    for (void* p : { (void*)s->nodes, (void*)s->prims, (void*)s->recs, (void*)s->orig_id, (void*)s->textures, (void*)s->dbg.keys,
+    for (void* p : { (void*)s->prims, (void*)s->recs, (void*)s->orig_id, (void*)s->textures, (void*)s->dbg.keys,
                      (void*)s->dbg.order, (void*)s->dbg.parent, (void*)s->dbg.left, (void*)s->dbg.right, (void*)s->dbg.node_min,
                      (void*)s->dbg.node_max, (void*)s->tree.left, (void*)s->tree.right, (void*)s->tree.node_min, (void*)s->tree.node_max, (void*)s->wnodes })
         if (p) drb_dev_free(p, st);
