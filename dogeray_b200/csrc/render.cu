@@ -816,6 +816,18 @@ int g_step_min = []() { const char* e = getenv("DOGERAY_B200_STEP_MIN"); int v =
 // on B200 the sort costs more than the ~5 % of traversal time it saves on the 1 M-triangle workload)
 long g_sort_min = []() { const char* e = getenv("DOGERAY_B200_SORT_MIN"); return e ? atol(e) : 0L; }();
 
+// device scratch that returns to the block cache when it goes out of scope, after its stream has drained
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) { cudaStreamSynchronize(st); drb_dev_free(p, st); } }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return drb_dev_alloc(&p, bytes, s); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 struct EventPool {
     std::vector<cudaEvent_t> ev;
     ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
@@ -958,23 +970,16 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
     if (int rc = check_settings(settings)) return rc;
     DRB_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)settings->width * settings->height * 3;
-    float* d = nullptr;
     drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
-    DRB_CUDA(drb_dev_alloc((void**)&d, n * sizeof(float), stream));
-    int rc = DRB_OK;
-    if (o.flags & DRB_FLAG_ACCUMULATE) {
-        if (cudaMemcpyAsync(d, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DRB_ERR_CUDA;
-    }
-    if (rc == DRB_OK) rc = render_core(s, settings, &o, settings->width, settings->height, 1, d, stats);
-    if (rc == DRB_OK) {
-        cudaError_t e = cudaMemcpyAsync(accum_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) { drb_set_error("download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
-    }
-    cudaStreamSynchronize(stream);
-    drb_dev_free(d, stream);
-    return rc;
+    DevBuf buf;
+    DRB_CUDA(buf.alloc(n * sizeof(float), stream));
+    float* d = buf.as<float>();
+    if (o.flags & DRB_FLAG_ACCUMULATE) DRB_CUDA(cudaMemcpyAsync(d, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    if (int rc = render_core(s, settings, &o, settings->width, settings->height, 1, d, stats)) return rc;
+    DRB_CUDA(cudaMemcpyAsync(accum_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    DRB_CUDA(cudaStreamSynchronize(stream));
+    return DRB_OK;
 }
 
 int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opts, int divisor, int32_t* out)
@@ -989,28 +994,22 @@ int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opt
     o.flags &= ~DRB_FLAG_ACCUMULATE;
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
     const uint32_t spp = o.sample_count ? o.sample_count : (uint32_t)std::max(settings->spp, 0);
-    float* d_acc = nullptr; int32_t* d_out = nullptr;
     const size_t nfull = (size_t)settings->width * settings->height * 3;
-    DRB_CUDA(drb_dev_alloc((void**)&d_acc, (size_t)W * H * 3 * sizeof(float), stream));
-    if (drb_dev_alloc((void**)&d_out, nfull * sizeof(int32_t), stream) != cudaSuccess) { drb_dev_free(d_acc, stream); drb_set_error("out of device memory"); return DRB_ERR_NOMEM; }
-    int rc = DRB_OK;
-    {
-        // entries outside the launched grid stay as the caller left them
-        cudaError_t e = cudaMemcpyAsync(d_out, out, nfull * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
-        if (e != cudaSuccess) { drb_set_error("upload failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
-    }
-    if (rc == DRB_OK) rc = render_core(s, settings, &o, W, H, divisor, d_acc, nullptr);
-    if (rc == DRB_OK) {
-        const float scale = (float)(1.0 / (double)(float)spp);          // kernel.cu:1081
-        dim3 block(8, 8), grid(W / 8, H / 8);
-        k_frame_i3<<<grid, block, 0, stream>>>(d_acc, W, H, settings->height, scale, d_out);
-        cudaError_t e = cudaMemcpyAsync(out, d_out, nfull * sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) { drb_set_error("frame download failed: %s", cudaGetErrorString(e)); rc = DRB_ERR_CUDA; }
-    }
-    cudaStreamSynchronize(stream);
-    drb_dev_free(d_acc, stream); drb_dev_free(d_out, stream);
-    return rc;
+    DevBuf b_acc, b_out;
+    DRB_CUDA(b_acc.alloc((size_t)W * H * 3 * sizeof(float), stream));
+    DRB_CUDA(b_out.alloc(nfull * sizeof(int32_t), stream));
+    float* d_acc = b_acc.as<float>();
+    int32_t* d_out = b_out.as<int32_t>();
+    // entries outside the launched grid stay as the caller left them
+    DRB_CUDA(cudaMemcpyAsync(d_out, out, nfull * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    if (int rc = render_core(s, settings, &o, W, H, divisor, d_acc, nullptr)) return rc;
+    const float scale = (float)(1.0 / (double)(float)spp);          // kernel.cu:1081
+    dim3 block(8, 8), grid(W / 8, H / 8);
+    k_frame_i3<<<grid, block, 0, stream>>>(d_acc, W, H, settings->height, scale, d_out);
+    DRB_CUDA(cudaGetLastError());
+    DRB_CUDA(cudaMemcpyAsync(out, d_out, nfull * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    DRB_CUDA(cudaStreamSynchronize(stream));
+    return DRB_OK;
 }
 
 int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int32_t* ids, float* t)
@@ -1023,24 +1022,24 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     RenderBuffers* rb = s->rb;
     Queues q = rb->q;
     cudaStream_t stream = s->stream;
-    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int32_t* d_ids = nullptr;
-    DRB_CUDA(drb_dev_alloc((void**)&d_o, (size_t)n * 12, stream));
-    DRB_CUDA(drb_dev_alloc((void**)&d_d, (size_t)n * 12, stream));
-    DRB_CUDA(drb_dev_alloc((void**)&d_t, (size_t)n * 4, stream));
-    DRB_CUDA(drb_dev_alloc((void**)&d_ids, (size_t)n * 4, stream));
-    cudaMemcpyAsync(d_o, o3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_d, d3, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
+    DevBuf b_o, b_d, b_t, b_ids;
+    DRB_CUDA(b_o.alloc((size_t)n * 12, stream));
+    DRB_CUDA(b_d.alloc((size_t)n * 12, stream));
+    DRB_CUDA(b_t.alloc((size_t)n * 4, stream));
+    DRB_CUDA(b_ids.alloc((size_t)n * 4, stream));
+    float *d_o = b_o.as<float>(), *d_d = b_d.as<float>(), *d_t = b_t.as<float>();
+    int32_t* d_ids = b_ids.as<int32_t>();
+    DRB_CUDA(cudaMemcpyAsync(d_o, o3, (size_t)n * 12, cudaMemcpyHostToDevice, stream));
+    DRB_CUDA(cudaMemcpyAsync(d_d, d3, (size_t)n * 12, cudaMemcpyHostToDevice, stream));
     const uint32_t nn = (uint32_t)n;
     k_load_rays<<<(nn + 255) / 256, 256, 0, stream>>>(d_o, d_d, nn, q);
     k_prepare<<<1, 32, 0, stream>>>(q.counters, -1, 0, nn);
     k_trace<<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(dev_scene(s), scene_scale(s), q, 0, g_refill, g_leaf_batch, g_step_min, nullptr);
     k_store_ids<<<(nn + 255) / 256, 256, 0, stream>>>(q.hit, s->orig_id, nn, d_ids, d_t);
-    cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
-    if (t) cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
-    cudaError_t e = cudaStreamSynchronize(stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    drb_dev_free(d_o, stream); drb_dev_free(d_d, stream); drb_dev_free(d_t, stream); drb_dev_free(d_ids, stream);
-    if (e != cudaSuccess) { drb_set_error("drb_trace_ids: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
+    DRB_CUDA(cudaGetLastError());
+    DRB_CUDA(cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+    if (t) DRB_CUDA(cudaMemcpyAsync(t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+    DRB_CUDA(cudaStreamSynchronize(stream));
     return DRB_OK;
 }
 
@@ -1059,17 +1058,16 @@ int drb_primary_rays(drb_scene* s, const drb_settings* settings, const drb_opts*
     if (int rc = ensure_buffers(s, nslots)) return rc;
     cudaStream_t stream = s->stream;
     const size_t n = (size_t)W * H * 3;
-    float *d_o = nullptr, *d_d = nullptr;
-    DRB_CUDA(drb_dev_alloc((void**)&d_o, n * 4, stream));
-    DRB_CUDA(drb_dev_alloc((void**)&d_d, n * 4, stream));
+    DevBuf b_o, b_d;
+    DRB_CUDA(b_o.alloc(n * 4, stream));
+    DRB_CUDA(b_d.alloc(n * 4, stream));
+    float *d_o = b_o.as<float>(), *d_d = b_d.as<float>();
     k_generate<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q);
     k_store_rays<<<(unsigned)((nslots + 255) / 256), 256, 0, stream>>>(fp, (uint32_t)nslots, s->rb->q, d_o, d_d);
-    cudaMemcpyAsync(o3, d_o, n * 4, cudaMemcpyDeviceToHost, stream);
-    cudaMemcpyAsync(d3, d_d, n * 4, cudaMemcpyDeviceToHost, stream);
-    cudaError_t e = cudaStreamSynchronize(stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    drb_dev_free(d_o, stream); drb_dev_free(d_d, stream);
-    if (e != cudaSuccess) { drb_set_error("drb_primary_rays: %s", cudaGetErrorString(e)); return DRB_ERR_CUDA; }
+    DRB_CUDA(cudaGetLastError());
+    DRB_CUDA(cudaMemcpyAsync(o3, d_o, n * 4, cudaMemcpyDeviceToHost, stream));
+    DRB_CUDA(cudaMemcpyAsync(d3, d_d, n * 4, cudaMemcpyDeviceToHost, stream));
+    DRB_CUDA(cudaStreamSynchronize(stream));
     return DRB_OK;
 }
 
