@@ -232,7 +232,21 @@ def ref_gpu_baseline(objs, st, spp_sample, rays_per_path):
             "host_parse_build_s": round(load_s, 2), "mean_pixel": float(out.mean())}
 
 
+def emit(line):
+    """the ONE line on the real stdout"""
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+REAL_STDOUT = 1
+
+
 def main():
+    # Libraries print banners to stdout (NCCL's version line, the reference's "N textures total"); keep the real
+    # stdout for the one JSON line and point file descriptor 1 at stderr for everything else.
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -266,7 +280,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": ncores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "rays_per_path": rpp, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     import numpy as np
@@ -411,7 +425,7 @@ def main():
                     line["ref_gpu"] = ref_gpu_baseline(objs, st, 4, rpp)
             except Exception as ex:
                 line["ref_gpu"] = {"unavailable": repr(ex)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
