@@ -806,7 +806,7 @@ int check_settings(const drb_settings* st)
 }
 
 // lanes-still-traversing threshold below which a warp refills its idle lanes (tunable for experiments)
-int g_refill = []() { const char* e = getenv("DOGERAY_B200_REFILL"); int v = e ? atoi(e) : 20; return v < 0 ? 0 : (v > 33 ? 33 : v); }();
+int g_refill = []() { const char* e = getenv("DOGERAY_B200_REFILL"); int v = e ? atoi(e) : 24; return v < 0 ? 0 : (v > 33 ? 33 : v); }();
 
 // stashed leaves are intersected when at least g_leaf_batch lanes hold one, or fewer than g_step_min lanes can descend
 int g_leaf_batch = []() { const char* e = getenv("DOGERAY_B200_LEAF_BATCH"); int v = e ? atoi(e) : 12; return v < 1 ? 1 : v; }();
