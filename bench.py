@@ -255,6 +255,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-spp", type=int, default=0, help="samples per pixel of the CPU baseline's bounded sample (0 = auto)")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / ref_gpu (profiling runs)")
+    ap.add_argument("--batch-paths", type=int, default=0, help="paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling runs only; invalidates the metric)")
     args = ap.parse_args()
     K, W = max(args.steps, 1), max(args.warmup, 0)
@@ -266,7 +267,7 @@ def main():
     ntris = int((objs["type"] == 2).sum())
     config = {"workload": desc, "triangles": ntris, "width": st.width, "height": st.height, "spp": st.spp, "max_depth": st.max_depth,
               "seed": 0, "sharding": "samples, contiguous ranges per rank, one NCCL reduce of the float radiance sums to rank 0" if world > 1 else "none",
-              "l2": "working set per step (ray queues ~1.4 GB per 16M-path batch + 240 MB scene) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "working set per step (ray queues: 120 B per path slot, up to 15 GB per batch; scene 220 MB) exceeds the 126 MB L2; no explicit flush"}
     ncores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -314,7 +315,7 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        s = scene.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, stream=stream, want_stats=True)
+        s = scene.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, batch_paths=args.batch_paths, stream=stream, want_stats=True)
         if world > 1:
             dist.reduce(accum, dst=0)
         return s
@@ -354,7 +355,7 @@ def main():
         t0 = time.perf_counter()
         sc = drb.Scene.from_host(hs, device=local)            # H2D of every object line + GPU LBVH build
         t1 = time.perf_counter()
-        s = sc.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, stream=stream, want_stats=True)
+        s = sc.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, batch_paths=args.batch_paths, stream=stream, want_stats=True)
         t2 = time.perf_counter()
         if world > 1:
             dist.reduce(accum, dst=0)

@@ -742,6 +742,10 @@ Camera make_camera(const drb_settings& st, int W, int H, int divisor)
     return c;
 }
 
+// reorder a bounce's rays before tracing when the queue holds at least this many (0 = never, the default:
+// on B200 the sort costs more than the ~5 % of traversal time it saves on the 1 M-triangle workload)
+long g_sort_min = []() { const char* e = getenv("DOGERAY_B200_SORT_MIN"); return e ? atol(e) : 0L; }();
+
 int ensure_buffers(drb_scene* s, size_t slots)
 {
     if (!s->rb) s->rb = new RenderBuffers();
@@ -759,13 +763,15 @@ int ensure_buffers(drb_scene* s, size_t slots)
     DRB_CUDA(drb_dev_alloc((void**)&q.hit, slots * sizeof(uint2), st));
     DRB_CUDA(drb_dev_alloc((void**)&q.contrib, slots * sizeof(float4), st));
     DRB_CUDA(drb_dev_alloc((void**)&q.counters, CNT_WORDS * sizeof(uint32_t), st));
-    for (int k = 0; k < 2; ++k) {
-        DRB_CUDA(drb_dev_alloc((void**)&rb->sort_keys[k], slots * sizeof(uint32_t), st));
-        DRB_CUDA(drb_dev_alloc((void**)&rb->sort_vals[k], slots * sizeof(uint32_t), st));
+    if (g_sort_min > 0) {                            // the opt-in ray reordering needs keys / indices / CUB scratch
+        for (int k = 0; k < 2; ++k) {
+            DRB_CUDA(drb_dev_alloc((void**)&rb->sort_keys[k], slots * sizeof(uint32_t), st));
+            DRB_CUDA(drb_dev_alloc((void**)&rb->sort_vals[k], slots * sizeof(uint32_t), st));
+        }
+        DRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, rb->sort_tmp_bytes, rb->sort_keys[0], rb->sort_keys[1], rb->sort_vals[0], rb->sort_vals[1],
+                                                 (int)std::min<size_t>(slots, 0x7FFFFFFF), 0, 24, st));
+        DRB_CUDA(drb_dev_alloc(&rb->sort_tmp, rb->sort_tmp_bytes ? rb->sort_tmp_bytes : 16, st));
     }
-    DRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, rb->sort_tmp_bytes, rb->sort_keys[0], rb->sort_keys[1], rb->sort_vals[0], rb->sort_vals[1],
-                                             (int)std::min<size_t>(slots, 0x7FFFFFFF), 0, 24, st));
-    DRB_CUDA(drb_dev_alloc(&rb->sort_tmp, rb->sort_tmp_bytes ? rb->sort_tmp_bytes : 16, st));
     DRB_CUDA(cudaMemsetAsync(q.counters, 0, CNT_WORDS * sizeof(uint32_t), st));
     DRB_CUDA(cudaStreamSynchronize(st));             // the buffers may be used from a caller-provided stream next
     rb->capacity = slots;
@@ -812,9 +818,7 @@ int g_refill = []() { const char* e = getenv("DOGERAY_B200_REFILL"); int v = e ?
 int g_leaf_batch = []() { const char* e = getenv("DOGERAY_B200_LEAF_BATCH"); int v = e ? atoi(e) : 12; return v < 1 ? 1 : v; }();
 int g_step_min = []() { const char* e = getenv("DOGERAY_B200_STEP_MIN"); int v = e ? atoi(e) : 20; return v < 1 ? 1 : v; }();
 
-// reorder a bounce's rays before tracing when the queue holds at least this many (0 = never, the default:
-// on B200 the sort costs more than the ~5 % of traversal time it saves on the 1 M-triangle workload)
-long g_sort_min = []() { const char* e = getenv("DOGERAY_B200_SORT_MIN"); return e ? atol(e) : 0L; }();
+
 
 // device scratch that returns to the block cache when it goes out of scope, after its stream has drained
 struct DevBuf {
@@ -845,11 +849,27 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
 
     const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
     const size_t slots_per_sample = (size_t)tiles_x * tiles_y * 32;
-    size_t want = o.batch_paths ? o.batch_paths : (size_t)(16u << 20);
-    uint32_t per_batch = (uint32_t)std::max<size_t>(1, want / slots_per_sample);
-    per_batch = std::min<uint32_t>(per_batch, std::max<uint32_t>(total_samples, 1u));
-    if (slots_per_sample * per_batch >= 0xFFFFFFF0ull) { drb_set_error("batch too large"); return DRB_ERR_ARG; }
-    if (int rc = ensure_buffers(s, slots_per_sample * per_batch)) return rc;
+    // Paths in flight per wavefront batch.  The last bounces of a batch hold few rays and run at the latency floor,
+    // so bigger batches amortise them (1080p, 1 M triangles: 16 M paths 509 ms per frame, 128 M paths 465 ms).  A path
+    // slot costs 120 B of queues; by default take 128 M slots (15 GB) but never more than a quarter of the device memory,
+    // and halve on allocation failure.
+    size_t want = o.batch_paths;
+    if (!want) {
+        want = (size_t)128 << 20;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::max<size_t>(std::min(want, (size_t)(0.25 * (double)total_b) / 120), (size_t)1 << 20);
+    }
+    uint32_t per_batch = 1;
+    for (;;) {
+        per_batch = (uint32_t)std::max<size_t>(1, want / slots_per_sample);
+        per_batch = std::min<uint32_t>(per_batch, std::max<uint32_t>(total_samples, 1u));
+        if (slots_per_sample * per_batch >= 0xFFFFFFF0ull) { want /= 2; continue; }
+        const int rc = ensure_buffers(s, slots_per_sample * per_batch);
+        if (rc == DRB_OK) break;
+        if (per_batch == 1) return rc;                  // not even one sample per pixel fits
+        cudaGetLastError();                              // out of memory: try half the batch
+        want = slots_per_sample * (size_t)(per_batch / 2);
+    }
     RenderBuffers* rb = s->rb;
     Queues q = rb->q;
 

@@ -156,7 +156,7 @@ typedef struct drb_opts {
     uint64_t seed;              /* Philox key */
     uint32_t sample_base;       /* first sample index of this call */
     uint32_t sample_count;      /* samples per pixel to trace in this call; 0 -> settings->spp */
-    uint32_t batch_paths;       /* paths in flight per wavefront batch; 0 -> default */
+    uint32_t batch_paths;       /* paths in flight per wavefront batch; 0 -> 128 M (15 GB of queues), at most 1/4 of device memory */
     uint32_t flags;             /* DRB_FLAG_* */
     void* stream;               /* cudaStream_t to launch on; NULL -> the scene's own stream */
 } drb_opts;
