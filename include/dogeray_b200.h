@@ -176,8 +176,10 @@ void drb_opts_default(drb_opts* out);
 /* Replaces the accumulate loop of main() (kernel.cu:2154-2224) and every CudaStarter call in
  * it: traces `sample_count` samples for every pixel and writes the SUM of radiance, row-major,
  * 3 floats per pixel, index (y*W + x)*3, linear, unclamped.  Divide by the sample count for the
- * mean.  accum_dev is a DEVICE pointer (W*H*3 floats); the call is asynchronous on opts->stream
- * unless `stats` is non-NULL, in which case it synchronises to fill it. */
+ * mean.  accum_dev is a DEVICE pointer (W*H*3 floats).  All work is enqueued on opts->stream (the caller's stream
+ * order is respected); the host reads one queue counter per bounce to size the next launches and to stop a batch
+ * early, so the call returns after the last batch has been enqueued, not necessarily finished: synchronise the
+ * stream (or pass `stats`, which synchronises to fill it) before reading accum_dev. */
 int drb_render_device(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_dev, drb_stats* stats);
 /* Same with a HOST accumulation buffer (synchronous; includes the device->host copy). */
 int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats);
