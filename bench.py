@@ -157,15 +157,37 @@ class StdoutToStderr:
         return False
 
 
+_SCENE_FILE = {}
+
+
+def scene_file(objs, st):
+    """the workload as a .rts text file in its own directory (written once; the reference only reads files)"""
+    import dogeray_b200 as drb
+    if "path" not in _SCENE_FILE:
+        tmp = tempfile.mkdtemp(prefix="drb_bench_")
+        path = os.path.join(tmp, "scene.rts")
+        t0 = time.time()
+        drb.write_rts(path, st, objs)
+        log("[bench] wrote %s (%.0f MB) in %.1f s" % (path, os.path.getsize(path) / 1e6, time.time() - t0))
+        _SCENE_FILE["path"], _SCENE_FILE["dir"] = path, tmp
+    return _SCENE_FILE["path"], _SCENE_FILE["dir"]
+
+
+def scene_file_cleanup():
+    if "path" in _SCENE_FILE:
+        try:
+            os.remove(_SCENE_FILE["path"]); os.rmdir(_SCENE_FILE["dir"])
+        except OSError:
+            pass
+        _SCENE_FILE.clear()
+
+
 def cpu_reference_arm(objs, st, desc, spp_sample, steps, warmup, threads):
     """the reference's host-compiled trace function (or the restatement) on a bounded sample: `spp_sample`
     samples per pixel of the same frame.  Returns (Mrays/s, ms per step, kind, rays per path)."""
-    import dogeray_b200 as drb
     from oracle import refhost, restated
-    tmp = tempfile.mkdtemp(prefix="drb_bench_")
-    path = os.path.join(tmp, "scene.rts")
+    path, tmp = scene_file(objs, st)
     t0 = time.time()
-    drb.write_rts(path, st, objs)
     s = st.replace(spp=spp_sample)
     if refhost.available():
         kind = "reference"
@@ -178,7 +200,7 @@ def cpu_reference_arm(objs, st, desc, spp_sample, steps, warmup, threads):
         eng = restated.Restated(path, "")
         eng.apply(s); eng.set_seed(0)
         frame = lambda base: eng.frame(1, base, threads)
-    log("[cpu %s] scene written + parsed + host BVH built in %.1f s" % (kind, time.time() - t0))
+    log("[cpu %s] scene parsed + host BVH built in %.1f s" % (kind, time.time() - t0))
     for w in range(warmup):
         frame(1000 + w)
     rays = 0; t1 = time.time()
@@ -186,10 +208,6 @@ def cpu_reference_arm(objs, st, desc, spp_sample, steps, warmup, threads):
         _, _, r = frame(k * spp_sample)
         rays += r
     dt = time.time() - t1
-    try:
-        os.remove(path); os.rmdir(tmp)
-    except OSError:
-        pass
     paths = st.width * st.height * spp_sample * steps
     return rays / dt / 1e6, dt / steps * 1e3, kind, rays / max(paths, 1)
 
@@ -207,12 +225,9 @@ def ref_gpu_baseline(objs, st, spp_sample, rays_per_path):
     L.refgpu_set_settings.argtypes = [C.c_void_p]
     L.refgpu_kernel_only.argtypes = [C.c_void_p, C.c_int, C.c_int]; L.refgpu_kernel_only.restype = C.c_float
     L.refgpu_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
-    tmp = tempfile.mkdtemp(prefix="drb_bench_")
-    path = os.path.join(tmp, "scene.rts")
-    drb.write_rts(path, st, objs)
+    path, tmp = scene_file(objs, st)
     t0 = time.time()
     n = L.refgpu_load(os.fsencode(path), os.fsencode(tmp))
-    os.remove(path); os.rmdir(tmp)
     if n <= 0:
         return {"unavailable": "refgpu_load returned %d" % n}
     load_s = time.time() - t0
@@ -281,6 +296,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": ncores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "rays_per_path": rpp, "gpu_launches": 0}
+        scene_file_cleanup()
         emit(line)
         return 0
 
@@ -426,6 +442,7 @@ def main():
                     line["ref_gpu"] = ref_gpu_baseline(objs, st, 4, rpp)
             except Exception as ex:
                 line["ref_gpu"] = {"unavailable": repr(ex)}
+            scene_file_cleanup()
         emit(line)
     if world > 1:
         dist.barrier()

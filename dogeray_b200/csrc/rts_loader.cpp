@@ -26,6 +26,7 @@
 #include <cstring>
 #include <filesystem>
 #include <mutex>
+#include <functional>
 #include <thread>
 
 #include <fcntl.h>
@@ -398,14 +399,35 @@ int drb_rts_write(const char* path, const drb_settings* s, const drb_object* obj
     fprintf(f, "*,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%s,%i,%i\n", s->cam[0], s->cam[1], s->cam[2], s->aperture,
             s->look[0], s->look[1], s->look[2], s->focus, (double)s->fov, (double)s->max_depth, (double)s->spp, s->bg_intensity,
             backtex_name ? backtex_name : texname(s->backtex), s->width, s->height);
-    for (int64_t i = 0; i < n; ++i) {
-        const drb_object& o = objs[i];
-        fprintf(f, "%f,%f,%f,%d,%f,%f,%f,%f,%g,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%s,%s\n",
+    // object lines are formatted in parallel, one contiguous range per thread, then written in order
+    auto format_range = [&](int64_t lo, int64_t hi, std::string& out) {
+        out.reserve((size_t)(hi - lo) * 400);
+        char line[1024];
+        for (int64_t i = lo; i < hi; ++i) {
+            const drb_object& o = objs[i];
+            const int k = snprintf(line, sizeof line,
+                "%f,%f,%f,%d,%f,%f,%f,%f,%g,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%s,%s\n",
                 o.pos[0], o.pos[1], o.pos[2], o.type, o.col[0], o.col[1], o.col[2], o.add_y, o.add_x,
                 o.dim[0], o.dim[1], o.dim[2], (double)o.mat, o.rot[0], o.rot[1], o.rot[2],
                 o.norm[0], o.norm[1], o.norm[2], o.n1[0], o.n1[1], o.n1[2], o.n2[0], o.n2[1], o.n2[2], o.n3[0], o.n3[1], o.n3[2],
                 o.t1[0], o.t1[1], o.t2[0], o.t2[1], o.t3[0], o.t3[1], (double)o.smooth, (double)o.checker,
                 texname(o.texnum), texname(o.rtexnum));
+            if (k > 0) out.append(line, (size_t)std::min<int>(k, (int)sizeof line - 1));
+        }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::min<int64_t>(hw ? hw : 4, std::max<int64_t>(1, n / 20000));
+    const int64_t chunk = 65536;                                  // bounded memory: format nthreads chunks at a time
+    for (int64_t base = 0; base < n; base += chunk * nthreads) {
+        std::vector<std::string> parts((size_t)nthreads);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) {
+            const int64_t lo = std::min(n, base + chunk * t), hi = std::min(n, lo + chunk);
+            if (lo < hi) pool.emplace_back(format_range, lo, hi, std::ref(parts[(size_t)t]));
+        }
+        for (auto& th : pool) th.join();
+        for (auto& part : parts)
+            if (!part.empty() && fwrite(part.data(), 1, part.size(), f) != part.size()) break;
     }
     bool ok = !ferror(f);
     ok = (fclose(f) == 0) && ok;
