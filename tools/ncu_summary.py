@@ -84,7 +84,7 @@ def kernel(src, dst, traffic_json=None):
         per = [to_bytes(d[ir], units[ir]) + to_bytes(d[iw], units[iw]) for d in data]
         json.dump({"source": src, "kernel": "k_trace", "launches_captured": len(per), "dram_bytes_each": per,
                    "dram_bytes_per_launch": sum(per) / len(per),
-                   "note": "dram__bytes_read.sum + dram__bytes_write.sum per captured k_trace launch (first bounces of one 16.6 M-path batch)"},
+                   "note": "dram__bytes_read.sum + dram__bytes_write.sum per captured k_trace launch (the first bounces of one wavefront batch, i.e. the largest launches of a frame)"},
                   open(traffic_json, "w"), indent=1)
 
 
