@@ -268,7 +268,10 @@ __global__ void k_refit(int n, const float4* __restrict__ lmin, const float4* __
 // the process repeats until one cluster is left.  All steps are deterministic (ties go to the lower
 // position; node ids come from a prefix sum, not from atomics), so oracle/lbvh_host.c reproduces the
 // topology bit for bit.
-constexpr int kPlocRadius = 16;
+#ifndef DRB_PLOC_RADIUS
+#define DRB_PLOC_RADIUS 16
+#endif
+constexpr int kPlocRadius = DRB_PLOC_RADIUS;
 
 __device__ __forceinline__ float union_half_area(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi)
 {
@@ -482,8 +485,8 @@ namespace {
 struct BlockCache {
     std::mutex mu;
     std::unordered_map<void*, size_t> live;                     // every block handed out -> its size
-    std::unordered_multimap<size_t, void*> idle[16];            // per device: size -> idle blocks
-    size_t idle_bytes[16] = { 0 };
+    std::unordered_map<int, std::unordered_multimap<size_t, void*>> idle;   // device -> (size -> idle blocks)
+    std::unordered_map<int, size_t> idle_bytes;
     static constexpr size_t kMaxIdleBytes = size_t(48) << 30;   // beyond this, blocks go back to the pool
 } g_cache;
 }
@@ -495,12 +498,12 @@ cudaError_t drb_dev_alloc(void** p, size_t bytes, cudaStream_t st)
     if (bytes == 0) bytes = 16;
     {
         std::lock_guard<std::mutex> g(g_cache.mu);
-        auto& idle = g_cache.idle[dev & 15];
+        auto& idle = g_cache.idle[dev];
         auto it = idle.find(bytes);
         if (it != idle.end()) {
             *p = it->second;
             idle.erase(it);
-            g_cache.idle_bytes[dev & 15] -= bytes;
+            g_cache.idle_bytes[dev] -= bytes;
             g_cache.live[*p] = bytes;
             return cudaSuccess;
         }
@@ -522,9 +525,9 @@ void drb_dev_free(void* p, cudaStream_t st)
         std::lock_guard<std::mutex> g(g_cache.mu);
         auto it = g_cache.live.find(p);
         if (it != g_cache.live.end()) { bytes = it->second; g_cache.live.erase(it); }
-        if (bytes && g_cache.idle_bytes[dev & 15] + bytes <= BlockCache::kMaxIdleBytes) {
-            g_cache.idle[dev & 15].emplace(bytes, p);
-            g_cache.idle_bytes[dev & 15] += bytes;
+        if (bytes && g_cache.idle_bytes[dev] + bytes <= BlockCache::kMaxIdleBytes) {
+            g_cache.idle[dev].emplace(bytes, p);
+            g_cache.idle_bytes[dev] += bytes;
             return;
         }
     }
