@@ -152,6 +152,7 @@ _sig("drb_free", None, _vp)
 _sig("drb_last_error", _cp)
 _sig("drb_abi_version", _i)
 _sig("drb_device_count", _i)
+_sig("drb_trim", _i, _i)
 _sig("drb_philox_word", _u32, _u64, _u32, _u32, _u32, _u32)
 
 EXPORTED_SYMBOLS = [
@@ -163,7 +164,7 @@ EXPORTED_SYMBOLS = [
     "drb_scene_lbvh", "drb_opts_default", "drb_render_device", "drb_render", "drb_frame_i3",
     "drb_trace_ids", "drb_primary_rays", "drb_tonemap", "drb_tonemap_device", "drb_write_bmp",
     "drb_write_ppm", "drb_read_ppm", "drb_free", "drb_last_error", "drb_abi_version",
-    "drb_device_count", "drb_philox_word",
+    "drb_device_count", "drb_trim", "drb_philox_word",
 ]
 
 
@@ -188,6 +189,11 @@ def default_settings() -> Settings:
 
 def device_count() -> int:
     return int(_lib.drb_device_count())
+
+
+def trim(device: int = 0):
+    """Return all idle device memory of `device` to the driver."""
+    _check(_lib.drb_trim(device))
 
 
 def philox_word(seed: int, x: int, y: int, sample: int, n: int) -> int:

@@ -534,6 +534,25 @@ void drb_dev_free(void* p, cudaStream_t st)
     cudaFreeAsync(p, st);
 }
 
+extern "C" int drb_trim(int device)
+{
+    DRB_CUDA(cudaSetDevice(device));
+    DRB_CUDA(cudaDeviceSynchronize());
+    std::vector<void*> blocks;
+    {
+        std::lock_guard<std::mutex> g(g_cache.mu);
+        for (auto& kv : g_cache.idle[device]) blocks.push_back(kv.second);
+        g_cache.idle[device].clear();
+        g_cache.idle_bytes[device] = 0;
+    }
+    for (void* p : blocks) DRB_CUDA(cudaFreeAsync(p, nullptr));
+    DRB_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    DRB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    DRB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return DRB_OK;
+}
+
 namespace {
 
 int retain_pool(int device)

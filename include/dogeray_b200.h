@@ -216,6 +216,9 @@ void drb_free(void* p);
 const char* drb_last_error(void);
 int drb_abi_version(void);
 int drb_device_count(void);
+/* Device memory is recycled through a block cache and the stream-ordered pool and is not returned to the driver
+ * when scenes are freed; this hands all idle memory of `device` back (call with no render in flight). */
+int drb_trim(int device);
 /* word `n` of the sampler stream of pixel (x, y), sample `sample` (Philox4x32-10) */
 uint32_t drb_philox_word(uint64_t seed, uint32_t x, uint32_t y, uint32_t sample, uint32_t n);
 

@@ -322,3 +322,16 @@ def test_all_material_classes_textures_and_env_map(tmp_path, maybe_ref):
     acc, stats = sc.render(stt, seed=13)
     assert stats.rays == rays
     assert_frames_match(acc.transpose(1, 0, 2) * np.float32(255.0) * np.float32(1.0 / 3), f)
+
+
+def test_trim_releases_cached_memory_and_rendering_still_works():
+    import torch
+    objs, st = synth.heightfield_scene(n=16, width=64, height=40, spp=2, max_depth=3)
+    hs = drb.HostScene.from_objects(objs, st)
+    sc = drb.Scene.from_host(hs); a, _ = sc.render(st, seed=1); sc.close()
+    free0, _ = torch.cuda.mem_get_info()
+    drb.trim(0)
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 >= free0
+    sc = drb.Scene.from_host(hs); b, _ = sc.render(st, seed=1); sc.close()
+    assert np.array_equal(a, b)
