@@ -74,6 +74,7 @@ def random_scene(rng, n, scale):
     o["type"][sph] = 0
     o["dim"][sph, 0] = rng.uniform(0.05, 0.4, int(sph.sum())) * scale
     o["mat"][sph & (o["mat"] == 4)] = 3                               # glass spheres need an inside hit the reference does not have
+    o["checker"][sph] = 0                                             # getnormal leaves texco uninitialised for spheres (kernel.cu:707-710): UB with the checker
     deg = rng.uniform(size=n) < 0.05                                  # zero-area triangles
     o["rot"][deg] = o["dim"][deg]
     dup = rng.uniform(size=n) < 0.05                                  # exact duplicates (all keys tie, equal t)
@@ -113,5 +114,9 @@ def test_random_scenes(tmp_path, maybe_ref, seed):
     acc, stats = sc.render(st, seed=seed)
     ours = acc.transpose(1, 0, 2) * np.float32(255.0) * np.float32(0.5)
     identical = float(np.mean(np.all(ours == f, axis=-1)))
-    assert identical >= 0.97, identical                                 # ties on duplicated objects may pick the twin with another material
+    rmse = float(np.sqrt(np.mean(((ours - f) / 255.0) ** 2)))
+    # spheres: hit_sphere's powf(len, 2) is x*x here (an ulp apart now and then), and exact-t ties on duplicated objects
+    # may pick the twin with another material -- so not every pixel is bit-identical, but nearly all are
+    assert stats.rays == rays
+    assert identical >= 0.97 and rmse < 0.02, (identical, rmse)
     assert np.isfinite(acc).all()
