@@ -53,3 +53,35 @@ def render_sharded(render_fn: Callable[[int, int], "object"], spp: int, rank: in
         else:
             dist.reduce(acc, dst=reduce_dst, op=dist.ReduceOp.SUM)
     return acc, count
+
+
+def render_progressive(render_fn: Callable[[int, int], "object"], spp: int, chunk: int, rank: int, world: int, sample_base: int = 0,
+                       reduce_dst: Optional[int] = 0):
+    """Progressive rendering with a periodic reduce: the headless, multi-GPU stand-in for the reference's
+    accumulate-and-redraw loop (kernel.cu:2154-2224).
+
+    The frame's `spp` sample indices are consumed `chunk` at a time; within a chunk every rank traces its contiguous
+    share (shard_samples) with render_fn(base, count) -> tensor of radiance SUMS, the chunk is reduced to `reduce_dst`
+    (all ranks if None) and added to the running total.  Yields (total, samples_done) after every chunk: on the
+    destination rank `total` is the sum over all samples so far (divide by samples_done for the mean image); other
+    ranks get their local partial and should only use the count.  One reduce of W*H*3 floats per chunk is the only
+    traffic between ranks.
+    """
+    import torch
+    import torch.distributed as dist
+    if chunk < 1:
+        raise ValueError("chunk must be >= 1")
+    total = None
+    done = 0
+    while done < spp:
+        n = min(chunk, spp - done)
+        base, count = shard_samples(n, rank, world, sample_base + done)
+        part = render_fn(base, count)
+        if world > 1:
+            if reduce_dst is None:
+                dist.all_reduce(part, op=dist.ReduceOp.SUM)
+            else:
+                dist.reduce(part, dst=reduce_dst, op=dist.ReduceOp.SUM)
+        total = part.clone() if total is None else total.add_(part)
+        done += n
+        yield total, done

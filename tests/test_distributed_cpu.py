@@ -32,7 +32,7 @@ import torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 import dogeray_b200 as drb
 from dogeray_b200 import synth
-from dogeray_b200.distributed import init_from_env, render_sharded
+from dogeray_b200.distributed import init_from_env, render_progressive, render_sharded
 from oracle import restated
 
 rank, world = init_from_env("gloo")
@@ -55,6 +55,16 @@ if rank == 0:
     err = float(np.abs(got - full).max())
     print("MAXERR %g" % err)
     assert err < 2e-3, err
+# progressive: 5 samples in chunks of 2 -> three snapshots; the last one is the whole frame again
+snaps = []
+for total, done in render_progressive(render, st.spp, 2, rank, world):
+    snaps.append(done)
+    last = total
+assert snaps == [2, 4, 5], snaps
+if rank == 0:
+    err = float(np.abs(last.numpy() / st.spp * 255.0 - full).max())
+    print("PROGRESSIVE_MAXERR %g" % err)
+    assert err < 2e-3, err
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -69,4 +79,4 @@ def test_two_rank_gloo_sample_sharding(tmp_path):
            "--master-port", "29533", str(script), ROOT, str(tmp_path)]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "MAXERR" in p.stdout
+    assert "MAXERR" in p.stdout and "PROGRESSIVE_MAXERR" in p.stdout
