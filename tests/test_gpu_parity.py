@@ -335,3 +335,28 @@ def test_trim_releases_cached_memory_and_rendering_still_works():
     assert free1 >= free0
     sc = drb.Scene.from_host(hs); b, _ = sc.render(st, seed=1); sc.close()
     assert np.array_equal(a, b)
+
+
+def test_converged_radiance_4096spp_rmse_and_psnr(tmp_path, maybe_ref):
+    """north_star's radiance bar, literally: <= 1e-3 per-pixel RMSE / >= 45 dB PSNR against a 4096-spp reference image
+    of the same scene and seed (the reference image comes from the oracle; both sides use the same Philox stream)"""
+    objs, st = synth.heightfield_scene(n=16, width=32, height=24, spp=4096, max_depth=6)
+    p = str(tmp_path / "conv.rts")
+    drb.write_rts(p, st, objs)
+    sc = drb.Scene.load(p)
+    orc = Oracle(p, "", maybe_ref)
+    orc.apply(st, 77)
+    f, _, rays = orc.frame()
+    ref_img = f.transpose(1, 0, 2) / 255.0                                  # mean radiance, (H, W, 3)
+    acc, stats = sc.render(st, seed=77)
+    img = acc / np.float32(4096)
+    rmse = float(np.sqrt(np.mean((img - ref_img) ** 2)))
+    peak = float(max(ref_img.max(), 1.0))
+    psnr = float("inf") if rmse == 0 else 20 * np.log10(peak / rmse)
+    assert stats.rays == rays
+    assert rmse <= 1e-3 and psnr >= 45.0, (rmse, psnr)
+    # and a 256-spp image with another seed is an unbiased estimate of the same picture (noise ~ 1/sqrt(256))
+    other, _ = sc.render(st.replace(spp=256), seed=78)
+    noisy = float(np.sqrt(np.mean((other / np.float32(256) - ref_img) ** 2)))
+    assert noisy < 0.08, noisy
+    assert abs(float((other / np.float32(256)).mean()) - float(ref_img.mean())) < 0.01
