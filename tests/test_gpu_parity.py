@@ -360,3 +360,26 @@ def test_converged_radiance_4096spp_rmse_and_psnr(tmp_path, maybe_ref):
     noisy = float(np.sqrt(np.mean((other / np.float32(256) - ref_img) ** 2)))
     assert noisy < 0.08, noisy
     assert abs(float((other / np.float32(256)).mean()) - float(ref_img.mean())) < 0.01
+
+
+def test_non_finite_coordinates_do_not_hang(tmp_path):
+    """NaN / inf vertices (a text file can say `nan`) must end in an image or an error code, never in a hang"""
+    import subprocess, sys
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+import dogeray_b200 as drb
+from dogeray_b200 import synth
+objs, st = synth.heightfield_scene(n=12, width=48, height=32, spp=2, max_depth=4)
+objs["pos"][5] = np.nan; objs["dim"][17, 1] = np.inf; objs["rot"][40] = -np.inf; objs["pos"][99, 0] = 3e38
+try:
+    sc = drb.Scene.from_host(drb.HostScene.from_objects(objs, st))
+    acc, stats = sc.render(st, seed=1)
+    ids, t = sc.trace_ids(np.array([[0, -5, 7]], np.float32), np.array([[0, 5, -7]], np.float32))
+    print("RENDERED", stats.rays, float(np.nanmean(acc)))
+except drb.DogerayError as e:
+    print("ERROR", e.status)
+""" % ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-1500:]
+    assert "RENDERED" in p.stdout or "ERROR" in p.stdout
