@@ -383,3 +383,28 @@ except drb.DogerayError as e:
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stderr[-1500:]
     assert "RENDERED" in p.stdout or "ERROR" in p.stdout
+
+
+def test_render_error_paths_return_codes():
+    import ctypes as C
+    objs, st = synth.heightfield_scene(n=4, width=16, height=8, spp=1, max_depth=2)
+    sc = drb.Scene.from_host(drb.HostScene.from_objects(objs, st))
+    dummy = np.zeros(16 * 8 * 3, np.float32)
+    for bad in (st.replace(width=0), st.replace(height=-3), st.replace(width=40000), st.replace(max_depth=-1)):
+        assert drb._lib.drb_render(sc.handle, C.byref(bad), None, dummy.ctypes.data, None) == drb.ERR_ARG
+        assert drb.last_error() != ""
+    with pytest.raises(drb.DogerayError) as e:
+        sc.render(st.replace(backtex=3))                      # the scene has no textures
+    assert e.value.status == drb.ERR_ARG and "backtex" in str(e.value)
+    assert drb._lib.drb_render(sc.handle, C.byref(st), None, None, None) == drb.ERR_ARG
+    assert drb._lib.drb_render(None, C.byref(st), None, None, None) == drb.ERR_ARG
+    assert drb._lib.drb_trace_ids(sc.handle, None, None, 5, None, None) == drb.ERR_ARG
+    assert drb._lib.drb_frame_i3(sc.handle, C.byref(st), None, 0, None) == drb.ERR_ARG
+    with pytest.raises(drb.DogerayError):
+        drb.Scene.from_host(drb.HostScene.from_objects(objs, st), device=99)
+    # spp = 0: a black accumulator, no rays
+    acc, stats = sc.render(st.replace(spp=0))
+    assert stats.rays == 0 and not acc.any()
+    # depth 0: every path ends black immediately (kernel.cu:793 loop does not run)
+    acc, stats = sc.render(st.replace(max_depth=0))
+    assert stats.rays == 0 and not acc.any()
