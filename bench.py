@@ -270,6 +270,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-spp", type=int, default=0, help="samples per pixel of the CPU baseline's bounded sample (0 = auto)")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / ref_gpu (profiling runs)")
+    ap.add_argument("--shard", default="samples", choices=["samples", "tiles"],
+                    help="N > 1: shard sample indices (default) or interleaved 8x4-pixel tiles (bit-identical to the 1-GPU image)")
     ap.add_argument("--batch-paths", type=int, default=0, help="paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling runs only; invalidates the metric)")
     args = ap.parse_args()
@@ -321,7 +323,11 @@ def main():
     log("[rank %d] scene: %d prims, %d nodes, height %d, upload %.1f ms, GPU LBVH build %.1f ms (host wall %.2f s)" %
         (rank, bi.nprims, bi.nnodes, bi.max_depth, bi.upload_ms, bi.build_ms, time.time() - t0))
 
-    base, count = shard_samples(st.spp, rank, world)
+    if args.shard == "tiles" and world > 1:
+        base, count, tile_kw = 0, st.spp, dict(tile_rank=rank, tile_count=world)
+        config["sharding"] = "interleaved 8x4-pixel tiles (tile t -> rank t mod N), one NCCL reduce of the disjoint partial images to rank 0"
+    else:
+        (base, count), tile_kw = shard_samples(st.spp, rank, world), {}
     accum = torch.zeros(st.height, st.width, 3, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -331,7 +337,9 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        s = scene.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, batch_paths=args.batch_paths, stream=stream, want_stats=True)
+        if tile_kw:
+            accum.zero_()
+        s = scene.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, batch_paths=args.batch_paths, stream=stream, want_stats=True, **tile_kw)
         if world > 1:
             dist.reduce(accum, dst=0)
         return s
@@ -371,7 +379,9 @@ def main():
         t0 = time.perf_counter()
         sc = drb.Scene.from_host(hs, device=local)            # H2D of every object line + GPU LBVH build
         t1 = time.perf_counter()
-        s = sc.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, batch_paths=args.batch_paths, stream=stream, want_stats=True)
+        if tile_kw:
+            accum.zero_()
+        s = sc.render_device(accum.data_ptr(), st, seed=0, sample_base=base, sample_count=count, batch_paths=args.batch_paths, stream=stream, want_stats=True, **tile_kw)
         t2 = time.perf_counter()
         if world > 1:
             dist.reduce(accum, dst=0)

@@ -82,6 +82,7 @@ class Opts(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64), ("sample_base", C.c_uint32), ("sample_count", C.c_uint32),
         ("batch_paths", C.c_uint32), ("flags", C.c_uint32), ("stream", C.c_void_p),
+        ("tile_rank", C.c_uint32), ("tile_count", C.c_uint32),
     ]
 
 
@@ -368,15 +369,16 @@ class Scene:
         return dict(child=child, boxes=boxes)
 
     @staticmethod
-    def _opts(seed=0, sample_base=0, sample_count=0, batch_paths=0, flags=0, stream=None) -> Opts:
+    def _opts(seed=0, sample_base=0, sample_count=0, batch_paths=0, flags=0, stream=None, tile_rank=0, tile_count=0) -> Opts:
         o = Opts()
         _lib.drb_opts_default(C.byref(o))
         o.seed, o.sample_base, o.sample_count, o.batch_paths, o.flags = seed, sample_base, sample_count, batch_paths, flags
         o.stream = stream
+        o.tile_rank, o.tile_count = tile_rank, tile_count
         return o
 
     def render(self, settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=0, batch_paths=0,
-               accumulate_into: Optional[np.ndarray] = None, want_stats=True) -> Tuple[np.ndarray, Optional[Stats]]:
+               accumulate_into: Optional[np.ndarray] = None, want_stats=True, tile_rank=0, tile_count=0) -> Tuple[np.ndarray, Optional[Stats]]:
         """Sum of radiance per pixel, float32 (H, W, 3), host buffers (device->host copy included)."""
         st = settings if settings is not None else self.settings
         flags = 0
@@ -385,17 +387,17 @@ class Scene:
             assert out.shape == (st.height, st.width, 3)
             flags |= FLAG_ACCUMULATE
         else:
-            out = np.empty((st.height, st.width, 3), np.float32)
-        o = self._opts(seed, sample_base, sample_count, batch_paths, flags)
+            out = np.zeros((st.height, st.width, 3), np.float32)
+        o = self._opts(seed, sample_base, sample_count, batch_paths, flags, None, tile_rank, tile_count)
         stats = Stats() if want_stats else None
         _check(_lib.drb_render(self._h, C.byref(st), C.byref(o), out.ctypes.data, C.byref(stats) if stats is not None else None))
         return out, stats
 
     def render_device(self, accum_ptr: int, settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=0,
-                      batch_paths=0, accumulate=False, stream: Optional[int] = None, want_stats=False) -> Optional[Stats]:
+                      batch_paths=0, accumulate=False, stream: Optional[int] = None, want_stats=False, tile_rank=0, tile_count=0) -> Optional[Stats]:
         """Same into a DEVICE buffer of H*W*3 float32 (e.g. torch tensor .data_ptr()); asynchronous unless want_stats."""
         st = settings if settings is not None else self.settings
-        o = self._opts(seed, sample_base, sample_count, batch_paths, FLAG_ACCUMULATE if accumulate else 0, stream)
+        o = self._opts(seed, sample_base, sample_count, batch_paths, FLAG_ACCUMULATE if accumulate else 0, stream, tile_rank, tile_count)
         stats = Stats() if want_stats else None
         _check(_lib.drb_render_device(self._h, C.byref(st), C.byref(o), accum_ptr, C.byref(stats) if stats is not None else None))
         return stats

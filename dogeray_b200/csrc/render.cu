@@ -55,6 +55,7 @@ struct Camera {
 struct FrameParams {
     int W, H;                           // pixel grid traced
     int tiles_x, tiles_y;               // 8x4 pixel tiles
+    uint32_t tile_rank, tile_count;     // this call traces the tiles t with t % tile_count == tile_rank (1 GPU: 0, 1)
     uint32_t samples;                   // samples per pixel in this batch
     uint32_t sample_base;               // global index of the batch's first sample
     uint64_t seed;
@@ -92,10 +93,10 @@ DRB_D bool slot_to_pixel(const FrameParams& fp, uint32_t slot, int& x, int& y, u
 {
     const uint32_t lane = slot & 31u, unit = slot >> 5;
     s = unit % fp.samples;
-    const uint32_t tile = unit / fp.samples;
+    const uint32_t tile = (unit / fp.samples) * fp.tile_count + fp.tile_rank;      // local tile -> image tile
     x = (int)(tile % (uint32_t)fp.tiles_x) * 8 + (int)(lane & 7u);
     y = (int)(tile / (uint32_t)fp.tiles_x) * 4 + (int)(lane >> 3);
-    return x < fp.W && y < fp.H;
+    return x < fp.W && y < fp.H && tile < (uint32_t)(fp.tiles_x * fp.tiles_y);
 }
 
 // ---- sampling helpers (kernel.cu:640-662, 988-994) ----------------------------------------------
@@ -620,7 +621,9 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, const float4* _
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= fp.W || y >= fp.H) return;
-    const uint32_t tile = (uint32_t)(y >> 2) * (uint32_t)fp.tiles_x + (uint32_t)(x >> 3);
+    const uint32_t gtile = (uint32_t)(y >> 2) * (uint32_t)fp.tiles_x + (uint32_t)(x >> 3);
+    if (gtile % fp.tile_count != fp.tile_rank) return;                              // another shard's pixel: left untouched
+    const uint32_t tile = gtile / fp.tile_count;
     const uint32_t lane = (uint32_t)((y & 3) * 8 + (x & 7));
     f3 sum = mk3(0.f);
     for (uint32_t s = 0; s < fp.samples; ++s) {
@@ -848,7 +851,11 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
     if (st->backtex >= s->ntextures) { drb_set_error("settings.backtex %d out of range (scene has %d textures)", st->backtex, s->ntextures); return DRB_ERR_ARG; }
 
     const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4;
-    const size_t slots_per_sample = (size_t)tiles_x * tiles_y * 32;
+    const uint32_t tile_count = o.tile_count ? o.tile_count : 1u, tile_rank = o.tile_count ? o.tile_rank : 0u;
+    if (tile_rank >= tile_count) { drb_set_error("tile_rank %u out of range (tile_count %u)", tile_rank, tile_count); return DRB_ERR_ARG; }
+    const size_t tiles_total = (size_t)tiles_x * tiles_y;
+    const size_t my_tiles = tiles_total > tile_rank ? (tiles_total - tile_rank + tile_count - 1) / tile_count : 0;
+    const size_t slots_per_sample = std::max<size_t>(my_tiles, 1) * 32;
     // Paths in flight per wavefront batch.  The last bounces of a batch hold few rays and run at the latency floor,
     // so bigger batches amortise them (1080p, 1 M triangles: 16 M paths 509 ms per frame, 128 M paths 465 ms).  A path
     // slot costs 120 B of queues; by default take 128 M slots (15 GB) but never more than a quarter of the device memory,
@@ -874,7 +881,7 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
     Queues q = rb->q;
 
     FrameParams fp;
-    fp.W = W; fp.H = H; fp.tiles_x = tiles_x; fp.tiles_y = tiles_y;
+    fp.W = W; fp.H = H; fp.tiles_x = tiles_x; fp.tiles_y = tiles_y; fp.tile_rank = tile_rank; fp.tile_count = tile_count;
     fp.seed = o.seed; fp.backtex = st->backtex; fp.bg_intensity = st->bg_intensity;
     fp.scene_scale = scene_scale(s);
     fp.cam = make_camera(*st, st->width, st->height, divisor);     // aspect and u/v denominators come from the FULL size
@@ -940,7 +947,15 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
         DRB_CUDA(cudaMemcpyAsync(&rays, q.counters + CNT_RAYS, 8, cudaMemcpyDeviceToHost, stream));
         DRB_CUDA(cudaStreamSynchronize(stream));
         memset(stats, 0, sizeof *stats);
-        stats->paths = (uint64_t)W * H * total_samples;
+        stats->paths = tile_count == 1 ? (uint64_t)W * H * total_samples : 0;   // with tile sharding the caller sums paths over shards
+        if (tile_count > 1) {
+            uint64_t px = 0;
+            for (size_t t = tile_rank; t < tiles_total; t += tile_count) {
+                const int tx = (int)(t % tiles_x) * 8, ty = (int)(t / tiles_x) * 4;
+                px += (uint64_t)std::min(8, W - tx) * (uint64_t)std::min(4, H - ty);
+            }
+            stats->paths = px * total_samples;
+        }
         stats->rays = rays;
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_begin, ev_end); stats->total_ms = ms;
@@ -995,7 +1010,8 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
     DevBuf buf;
     DRB_CUDA(buf.alloc(n * sizeof(float), stream));
     float* d = buf.as<float>();
-    if (o.flags & DRB_FLAG_ACCUMULATE) DRB_CUDA(cudaMemcpyAsync(d, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    // accumulate adds to the caller's values; with tile sharding the pixels of other shards must come back as they were
+    if ((o.flags & DRB_FLAG_ACCUMULATE) || o.tile_count > 1) DRB_CUDA(cudaMemcpyAsync(d, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
     if (int rc = render_core(s, settings, &o, settings->width, settings->height, 1, d, stats)) return rc;
     DRB_CUDA(cudaMemcpyAsync(accum_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
     DRB_CUDA(cudaStreamSynchronize(stream));
@@ -1070,7 +1086,7 @@ int drb_primary_rays(drb_scene* s, const drb_settings* settings, const drb_opts*
     DRB_CUDA(cudaSetDevice(s->device));
     const int W = settings->width, H = settings->height;
     FrameParams fp;
-    fp.W = W; fp.H = H; fp.tiles_x = (W + 7) / 8; fp.tiles_y = (H + 3) / 4;
+    fp.W = W; fp.H = H; fp.tiles_x = (W + 7) / 8; fp.tiles_y = (H + 3) / 4; fp.tile_rank = 0; fp.tile_count = 1;
     fp.samples = 1; fp.sample_base = sample; fp.seed = opts ? opts->seed : 0;
     fp.backtex = -1; fp.bg_intensity = 1; fp.scene_scale = scene_scale(s);
     fp.cam = make_camera(*settings, W, H, 1);

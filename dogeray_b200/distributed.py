@@ -22,6 +22,15 @@ def shard_samples(spp: int, rank: int, world: int, base: int = 0) -> Tuple[int, 
     return base + start, count
 
 
+def shard_tiles(rank: int, world: int) -> Tuple[int, int]:
+    """Interleaved tile sharding: rank r traces the 8x4-pixel tiles t with t % world == r (drb_opts.tile_rank /
+    tile_count).  Every pixel's samples stay on one GPU in sample order, so the reduced image is bit-identical to
+    the single-GPU image; neighbouring tiles go to different ranks, which balances the load."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad shard request rank=%d world=%d" % (rank, world))
+    return rank, world
+
+
 def env_rank_world() -> Tuple[int, int, int]:
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 

@@ -29,7 +29,7 @@ def test_abi_version_and_struct_sizes():
     assert drb._lib.drb_abi_version() == 1
     assert ctypes.sizeof(drb.Settings) == 60
     assert drb.OBJECT_DTYPE.itemsize == 156
-    assert ctypes.sizeof(drb.Opts) == 32
+    assert ctypes.sizeof(drb.Opts) == 40
     assert ctypes.sizeof(drb.Stats) == 32
 
 

@@ -408,3 +408,20 @@ def test_render_error_paths_return_codes():
     # depth 0: every path ends black immediately (kernel.cu:793 loop does not run)
     acc, stats = sc.render(st.replace(max_depth=0))
     assert stats.rays == 0 and not acc.any()
+
+
+def test_tile_sharding_is_bit_identical_to_the_whole_image():
+    """interleaved 8x4-pixel tiles over 3 "ranks": the partial images are disjoint and their sum IS the 1-GPU image"""
+    objs, st = synth.heightfield_scene(n=20, width=70, height=45, spp=5, max_depth=5)      # not a multiple of the tile size
+    sc = drb.Scene.from_host(drb.HostScene.from_objects(objs, st))
+    full, sf = sc.render(st, seed=8)
+    parts, rays, paths = [], 0, 0
+    for r in range(3):
+        p, s = sc.render(st, seed=8, tile_rank=r, tile_count=3)
+        parts.append(p); rays += s.rays; paths += s.paths
+    assert rays == sf.rays and paths == sf.paths
+    nz = [(p != 0).any(axis=2) for p in parts]
+    assert not (nz[0] & nz[1]).any() and not (nz[0] & nz[2]).any() and not (nz[1] & nz[2]).any()      # disjoint pixels
+    assert np.array_equal(parts[0] + parts[1] + parts[2], full)                                        # bit-identical
+    with pytest.raises(drb.DogerayError):
+        sc.render(st, tile_rank=3, tile_count=3)
