@@ -233,7 +233,7 @@ class HostScene:
         return cls(h)
 
     def close(self):
-        if self._h:
+        if self._h and _lib is not None:             # _lib is None while the interpreter shuts down
             _lib.drb_host_scene_free(self._h)
             self._h = None
 
@@ -312,7 +312,7 @@ class Scene:
         return cls(h)
 
     def close(self):
-        if self._h:
+        if self._h and _lib is not None:             # _lib is None while the interpreter shuts down
             _lib.drb_scene_free(self._h)
             self._h = None
 
