@@ -116,6 +116,8 @@ _pp = C.POINTER(C.c_void_p)
 
 # every symbol include/dogeray_b200.h declares
 _sig("drb_host_scene_load", _i, _cp, _cp, _pp)
+_sig("drb_host_scene_load_cached", _i, _cp, _cp, _cp, _pp, C.POINTER(C.c_int))
+_sig("drb_hash_bytes", _u64, _vp, C.c_size_t)
 _sig("drb_host_scene_parse", _i, _cp, C.c_size_t, _cp, _pp)
 _sig("drb_host_scene_create", _i, C.POINTER(Settings), _vp, _i64, C.POINTER(_cp), _i, _pp)
 _sig("drb_host_scene_free", None, _vp)
@@ -157,7 +159,8 @@ _sig("drb_trim", _i, _i)
 _sig("drb_philox_word", _u32, _u64, _u32, _u32, _u32, _u32)
 
 EXPORTED_SYMBOLS = [
-    "drb_host_scene_load", "drb_host_scene_parse", "drb_host_scene_create", "drb_host_scene_free",
+    "drb_host_scene_load", "drb_host_scene_load_cached", "drb_hash_bytes", "drb_host_scene_parse", "drb_host_scene_create",
+    "drb_host_scene_free",
     "drb_host_scene_num_objects", "drb_host_scene_objects", "drb_host_scene_settings",
     "drb_host_scene_num_textures", "drb_host_scene_texture_path", "drb_host_scene_num_skipped",
     "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_create_ex", "drb_scene_tree", "drb_scene_wide", "drb_scene_load", "drb_scene_free",
@@ -192,6 +195,11 @@ def device_count() -> int:
     return int(_lib.drb_device_count())
 
 
+def hash_bytes(data: bytes) -> int:
+    """the 64-bit content hash the scene cache is keyed by"""
+    return int(_lib.drb_hash_bytes(data, len(data)))
+
+
 def trim(device: int = 0):
     """Return all idle device memory of `device` to the driver."""
     _check(_lib.drb_trim(device))
@@ -212,10 +220,20 @@ class HostScene:
         self._h = handle
 
     @classmethod
-    def load(cls, rts_path: str, tex_dir: Optional[str] = None) -> "HostScene":
+    def load(cls, rts_path: str, tex_dir: Optional[str] = None, cache=None) -> "HostScene":
+        """`cache`: None = parse the text; True = binary cache next to the scene (`<scene>.drbcache`);
+        a path = that cache file.  `cache_hit` on the result says whether the cache served the load."""
         h = C.c_void_p()
-        _check(_lib.drb_host_scene_load(_b(rts_path), _b(tex_dir), C.byref(h)))
-        return cls(h)
+        if cache is None or cache is False:
+            _check(_lib.drb_host_scene_load(_b(rts_path), _b(tex_dir), C.byref(h)))
+            hs = cls(h)
+            hs.cache_hit = False
+            return hs
+        hit = C.c_int(0)
+        _check(_lib.drb_host_scene_load_cached(_b(rts_path), _b(tex_dir), None if cache is True else _b(cache), C.byref(h), C.byref(hit)))
+        hs = cls(h)
+        hs.cache_hit = bool(hit.value)
+        return hs
 
     @classmethod
     def parse(cls, text: bytes, tex_dir: Optional[str] = None) -> "HostScene":

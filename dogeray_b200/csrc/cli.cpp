@@ -29,6 +29,7 @@ int main(int argc, char** argv)
     std::string scene_path = "scene.rts", out_path;
     std::string save_acc, resume_acc;
     int spp = -1, depth = -1, w = -1, h = -1, device = 0, snapshot_every = 0;
+    bool use_cache = false;
     unsigned long long seed = 0;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -44,17 +45,22 @@ int main(int argc, char** argv)
         else if (a == "--snapshot-every") snapshot_every = atoi(next("--snapshot-every"));
         else if (a == "--save-acc") save_acc = next("--save-acc");
         else if (a == "--resume") resume_acc = next("--resume");
+        else if (a == "--cache") use_cache = true;
         else if (a == "--res") { if (sscanf(next("--res"), "%dx%d", &w, &h) != 2) { fprintf(stderr, "dogeray-b200: --res wants WxH\n"); return 2; } }
         else if (a == "-h" || a == "--help") {
             printf("usage: dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]\n"
-                   "                    [--snapshot-every N] [--save-acc file.acc] [--resume file.acc]\n");
+                   "                    [--snapshot-every N] [--save-acc file.acc] [--resume file.acc] [--cache]\n"
+                   "  --cache  keep the parsed scene in <scene>.drbcache (keyed by a hash of the text) and reuse it\n");
             return 0;
         } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "dogeray-b200: unknown option %s\n", a.c_str()); return 2; }
         else scene_path = a;
     }
     printf("Opening:%s\n", scene_path.c_str());
     drb_host_scene* hs = nullptr;
-    if (drb_host_scene_load(scene_path.c_str(), nullptr, &hs) != DRB_OK) return fail("cannot load scene");
+    int cache_hit = 0;
+    if ((use_cache ? drb_host_scene_load_cached(scene_path.c_str(), nullptr, nullptr, &hs, &cache_hit)
+                   : drb_host_scene_load(scene_path.c_str(), nullptr, &hs)) != DRB_OK) return fail("cannot load scene");
+    if (use_cache) printf("scene cache: %s\n", cache_hit ? "hit" : "miss (written)");
     printf("%lld tris\n%d textures total\n", (long long)drb_host_scene_num_objects(hs), drb_host_scene_num_textures(hs));
     if (drb_host_scene_num_skipped(hs)) fprintf(stderr, "dogeray-b200: warning: %s\n", drb_last_error());
     drb_scene* scene = nullptr;

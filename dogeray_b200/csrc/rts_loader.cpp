@@ -271,6 +271,134 @@ int parse_buffer(const char* text, size_t len, const char* tex_dir, drb_host_sce
     return DRB_OK;
 }
 
+
+// ---- binary scene cache ("optional binary cache keyed by file hash") -------------------
+// 64-bit content hash: 1 MiB chunks hashed independently (multiply-fold over 8-byte words, threads over
+// chunks), chunk hashes folded in order.  Not cryptographic; it only has to notice an edited scene file.
+inline uint64_t fold64(uint64_t a, uint64_t b)
+{
+    unsigned __int128 r = (unsigned __int128)a * b;
+    return (uint64_t)r ^ (uint64_t)(r >> 64);
+}
+constexpr uint64_t kHashK0 = 0x9E3779B97F4A7C15ull, kHashK1 = 0xD6E8FEB86659FD93ull;
+constexpr size_t kHashChunk = size_t(1) << 20;
+
+uint64_t hash_chunk(const unsigned char* p, size_t n, uint64_t index)
+{
+    uint64_t h = fold64(index + kHashK0, n ^ kHashK1);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, p + i, 8); h = fold64(h ^ w, kHashK0) + kHashK1; }
+    if (i < n) { uint64_t w = 0; memcpy(&w, p + i, n - i); h = fold64(h ^ w, kHashK1) + kHashK0; }
+    return h;
+}
+
+uint64_t hash_bytes(const void* data, size_t len)
+{
+    const unsigned char* p = (const unsigned char*)data;
+    const size_t nchunks = (len + kHashChunk - 1) / kHashChunk;
+    std::vector<uint64_t> hc(nchunks);
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t c = lo; c < hi; ++c) hc[c] = hash_chunk(p + c * kHashChunk, std::min(kHashChunk, len - c * kHashChunk), c);
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = std::min<size_t>(hw ? hw : 4, std::max<size_t>(1, nchunks / 8));
+    if (nthreads <= 1) work(0, nchunks);
+    else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nthreads; ++t) pool.emplace_back(work, nchunks * t / nthreads, nchunks * (t + 1) / nthreads);
+        for (auto& th : pool) th.join();
+    }
+    uint64_t h = fold64(len ^ kHashK1, kHashK0);
+    for (uint64_t c : hc) h = fold64(h ^ c, kHashK0) + kHashK1;
+    return h;
+}
+
+// texture ids inside objects and settings.backtex are indices into the scanned texture list, so the list is
+// part of the key
+uint64_t hash_tex_list(const std::vector<std::string>& tex)
+{
+    std::string all;
+    for (const auto& t : tex) { all += t; all.push_back('\0'); }
+    return hash_bytes(all.data(), all.size());
+}
+
+struct CacheHeader {
+    char magic[8];                 // "DRBSCN01"
+    uint32_t abi_version, sizeof_object, sizeof_settings, warning_len;
+    uint64_t source_hash, source_len, tex_hash, nobjects;
+    int64_t skipped;
+    drb_settings settings;
+    uint32_t pad;
+};
+static_assert(sizeof(CacheHeader) % 8 == 0, "objects follow the header and the warning text 8-byte aligned");
+const char kCacheMagic[8] = { 'D', 'R', 'B', 'S', 'C', 'N', '0', '1' };
+
+// returns a scene on a hit, nullptr on any mismatch or damage (the caller then parses the text)
+drb_host_scene* cache_read(const std::string& path, uint64_t source_hash, uint64_t source_len, const std::vector<std::string>& tex)
+{
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return nullptr;
+    struct stat st;
+    drb_host_scene* hs = nullptr;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && (size_t)st.st_size >= sizeof(CacheHeader)) {
+        size_t len = (size_t)st.st_size;
+        void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            CacheHeader h;
+            memcpy(&h, m, sizeof h);
+            size_t wl = ((size_t)h.warning_len + 7) & ~size_t(7);
+            bool ok = memcmp(h.magic, kCacheMagic, 8) == 0 && h.abi_version == (uint32_t)DRB_ABI_VERSION &&
+                      h.sizeof_object == sizeof(drb_object) && h.sizeof_settings == sizeof(drb_settings) &&
+                      h.source_hash == source_hash && h.source_len == source_len && h.tex_hash == hash_tex_list(tex) &&
+                      h.warning_len < (1u << 20) && h.nobjects <= (len - sizeof h) / sizeof(drb_object) &&
+                      len == sizeof h + wl + (size_t)h.nobjects * sizeof(drb_object);
+            if (ok) {
+                hs = new drb_host_scene();
+                hs->settings = h.settings;
+                hs->tex_paths = tex;
+                hs->skipped = h.skipped;
+                const char* q = (const char*)m + sizeof h;
+                hs->first_warning.assign(q, h.warning_len);
+                const drb_object* o = (const drb_object*)(q + wl);
+                hs->objects.assign(o, o + h.nobjects);
+            }
+            munmap(m, len);
+        }
+    }
+    close(fd);
+    return hs;
+}
+
+// best effort: a cache that cannot be written is not an error of the load
+bool cache_write(const std::string& path, const drb_host_scene& hs, uint64_t source_hash, uint64_t source_len)
+{
+    CacheHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, kCacheMagic, 8);
+    h.abi_version = (uint32_t)DRB_ABI_VERSION;
+    h.sizeof_object = (uint32_t)sizeof(drb_object);
+    h.sizeof_settings = (uint32_t)sizeof(drb_settings);
+    h.warning_len = (uint32_t)std::min<size_t>(hs.first_warning.size(), (1u << 20) - 1);
+    h.source_hash = source_hash; h.source_len = source_len;
+    h.tex_hash = hash_tex_list(hs.tex_paths);
+    h.nobjects = hs.objects.size();
+    h.skipped = hs.skipped;
+    h.settings = hs.settings;
+    std::string tmp = path + ".tmp." + std::to_string((long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    static const char zeros[8] = { 0 };
+    size_t wl = ((size_t)h.warning_len + 7) & ~size_t(7);
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    if (ok && h.warning_len) ok = fwrite(hs.first_warning.data(), 1, h.warning_len, f) == h.warning_len;
+    if (ok && wl > h.warning_len) ok = fwrite(zeros, 1, wl - h.warning_len, f) == wl - h.warning_len;
+    if (ok && h.nobjects) ok = fwrite(hs.objects.data(), sizeof(drb_object), (size_t)h.nobjects, f) == (size_t)h.nobjects;
+    ok = (fclose(f) == 0) && ok;
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;      // readers never see a half-written file
+    if (!ok) unlink(tmp.c_str());
+    return ok;
+}
+
 } // namespace
 
 void drb_set_error(const char* fmt, ...)
@@ -352,6 +480,41 @@ int drb_host_scene_load(const char* rts_path, const char* tex_dir, drb_host_scen
         rc = parse_buffer((const char*)m, len, tex_dir, out);
         munmap(m, len);
     }
+    close(fd);
+    return rc;
+}
+
+uint64_t drb_hash_bytes(const void* data, size_t len) { return (data || !len) ? hash_bytes(data, len) : 0; }
+
+int drb_host_scene_load_cached(const char* rts_path, const char* tex_dir, const char* cache_path, drb_host_scene** out, int* cache_hit)
+{
+    if (!rts_path || !out) { drb_set_error("drb_host_scene_load_cached: null argument"); return DRB_ERR_ARG; }
+    drb_clear_error();
+    *out = nullptr;
+    if (cache_hit) *cache_hit = 0;
+    std::string cpath = (cache_path && cache_path[0]) ? std::string(cache_path) : std::string(rts_path) + ".drbcache";
+    int fd = open(rts_path, O_RDONLY);
+    if (fd < 0) { drb_set_error("cannot open scene file '%s': %s", rts_path, strerror(errno)); return DRB_ERR_IO; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); drb_set_error("'%s' is not a regular file", rts_path); return DRB_ERR_IO; }
+    size_t len = (size_t)st.st_size;
+    void* m = nullptr;
+    if (len) {
+        m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); drb_set_error("mmap of '%s' failed: %s", rts_path, strerror(errno)); return DRB_ERR_IO; }
+    }
+    const uint64_t h = hash_bytes(m, len);
+    int rc = DRB_OK;
+    drb_host_scene* hs = cache_read(cpath, h, len, drb_scan_textures(tex_dir));
+    if (hs) {
+        if (cache_hit) *cache_hit = 1;
+        if (!hs->first_warning.empty()) drb_set_error("%s", hs->first_warning.c_str());
+        *out = hs;
+    } else {
+        rc = parse_buffer(len ? (const char*)m : "", len, tex_dir, out);
+        if (rc == DRB_OK) cache_write(cpath, **out, h, len);
+    }
+    if (m) munmap(m, len);
     close(fd);
     return rc;
 }

@@ -87,6 +87,15 @@ typedef struct drb_host_scene drb_host_scene;
  * contains "ppm"/"PPM" (NULL -> current working directory, as the reference does), visited in
  * sorted order; the lower-cased path must contain the (unmodified) query, kernel.cu:1172-1183. */
 int drb_host_scene_load(const char* rts_path, const char* tex_dir, drb_host_scene** out);
+/* drb_host_scene_load through a binary cache.  The cache file (`cache_path`, NULL ->
+ * rts_path + ".drbcache") holds the parsed objects and settings keyed by a 64-bit hash of the scene text, its
+ * length, the scanned texture list (texture ids are indices into it) and the ABI version; on any mismatch or
+ * damage the text is parsed and the cache rewritten (atomically; failing to write it is not an error).  A hit
+ * returns exactly what drb_host_scene_load returns.  *cache_hit (may be NULL) says which happened. */
+int drb_host_scene_load_cached(const char* rts_path, const char* tex_dir, const char* cache_path,
+                               drb_host_scene** out, int* cache_hit);
+/* the content hash the cache is keyed by (chunked multiply-fold, not cryptographic) */
+uint64_t drb_hash_bytes(const void* data, size_t len);
 /* Same from a memory buffer holding .rts text. */
 int drb_host_scene_parse(const char* text, size_t len, const char* tex_dir, drb_host_scene** out);
 /* Build one from arrays (synthetic scenes).  `tex_paths` may be NULL when ntex == 0. */

@@ -35,6 +35,17 @@ def test_cli_without_gpu_has_no_fallback(tmp_path):
     assert not os.path.exists(tmp_path / "scene.rts.bmp")
 
 
+def test_cli_cache_flag_writes_then_hits(tmp_path):
+    """--cache goes through drb_host_scene_load_cached before any CUDA call, so it is observable without a GPU"""
+    objs, st = synth.heightfield_scene(n=4, width=16, height=8, spp=1)
+    drb.write_rts(str(tmp_path / "scene.rts"), st, objs)
+    p = subprocess.run([CLI, "--cache"], capture_output=True, text=True, cwd=tmp_path)
+    assert "scene cache: miss (written)" in p.stdout and os.path.exists(tmp_path / "scene.rts.drbcache")
+    p = subprocess.run([CLI, "--cache"], capture_output=True, text=True, cwd=tmp_path)
+    assert "scene cache: hit" in p.stdout and "%d tris" % len(objs) in p.stdout
+    assert p.returncode == (0 if drb.device_count() > 0 else 1)
+
+
 @pytest.mark.gpu
 def test_cli_renders_the_same_image_as_the_library(tmp_path):
     objs, st = synth.heightfield_scene(n=16, width=64, height=40, spp=3, max_depth=4)
