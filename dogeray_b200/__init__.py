@@ -143,6 +143,7 @@ _sig("drb_scene_lbvh", _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 _sig("drb_opts_default", None, C.POINTER(Opts))
 _sig("drb_render_device", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _vp, C.POINTER(Stats))
 _sig("drb_render", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _vp, C.POINTER(Stats))
+_sig("drb_render_multi", _i, C.POINTER(C.c_void_p), _i, C.POINTER(Settings), C.POINTER(Opts), _vp, C.POINTER(Stats))
 _sig("drb_frame_i3", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _i, _vp)
 _sig("drb_trace_ids", _i, _vp, _vp, _vp, _i64, _vp, _vp)
 _sig("drb_primary_rays", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _u32, _vp, _vp)
@@ -165,7 +166,7 @@ EXPORTED_SYMBOLS = [
     "drb_host_scene_num_textures", "drb_host_scene_texture_path", "drb_host_scene_num_skipped",
     "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_create_ex", "drb_scene_tree", "drb_scene_wide", "drb_scene_load", "drb_scene_free",
     "drb_scene_settings", "drb_scene_num_prims", "drb_scene_num_objects", "drb_scene_build_info",
-    "drb_scene_lbvh", "drb_opts_default", "drb_render_device", "drb_render", "drb_frame_i3",
+    "drb_scene_lbvh", "drb_opts_default", "drb_render_device", "drb_render", "drb_render_multi", "drb_frame_i3",
     "drb_trace_ids", "drb_primary_rays", "drb_tonemap", "drb_tonemap_device", "drb_write_bmp",
     "drb_write_ppm", "drb_read_ppm", "drb_free", "drb_last_error", "drb_abi_version",
     "drb_device_count", "drb_trim", "drb_philox_word",
@@ -193,6 +194,26 @@ def default_settings() -> Settings:
 
 def device_count() -> int:
     return int(_lib.drb_device_count())
+
+
+def render_multi(scenes: Sequence["Scene"], settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=0,
+                 batch_paths=0, accumulate_into: Optional[np.ndarray] = None) -> Tuple[np.ndarray, Stats]:
+    """One frame over several resident scenes (the same scene on different devices) from this process: interleaved
+    tile sharding, one host thread per handle, merged on the host; bit-identical to Scene.render on one handle."""
+    assert len(scenes) >= 1
+    st = settings if settings is not None else scenes[0].settings
+    flags = 0
+    if accumulate_into is not None:
+        out = np.ascontiguousarray(accumulate_into, dtype=np.float32)
+        assert out.shape == (st.height, st.width, 3)
+        flags |= FLAG_ACCUMULATE
+    else:
+        out = np.zeros((st.height, st.width, 3), np.float32)
+    o = Scene._opts(seed, sample_base, sample_count, batch_paths, flags, None, 0, 0)
+    handles = (C.c_void_p * len(scenes))(*[sc.handle for sc in scenes])
+    stats = Stats()
+    _check(_lib.drb_render_multi(handles, len(scenes), C.byref(st), C.byref(o), out.ctypes.data, C.byref(stats)))
+    return out, stats
 
 
 def hash_bytes(data: bytes) -> int:

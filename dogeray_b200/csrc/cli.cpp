@@ -30,6 +30,7 @@ int main(int argc, char** argv)
     std::string save_acc, resume_acc;
     int spp = -1, depth = -1, w = -1, h = -1, device = 0, snapshot_every = 0;
     bool use_cache = false;
+    std::vector<int> devices;                        // --gpus N = 0..N-1, --devices a,b,c = exactly those (repeats allowed)
     unsigned long long seed = 0;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -41,6 +42,24 @@ int main(int argc, char** argv)
         else if (a == "--depth") depth = atoi(next("--depth"));
         else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
         else if (a == "--device") device = atoi(next("--device"));
+        else if (a == "--gpus") {
+            int n = atoi(next("--gpus"));
+            if (n < 1) { fprintf(stderr, "dogeray-b200: --gpus wants a positive count\n"); return 2; }
+            devices.clear();
+            for (int k = 0; k < n; ++k) devices.push_back(k);
+        } else if (a == "--devices") {
+            devices.clear();
+            const char* p = next("--devices");
+            while (*p) {
+                char* e = nullptr;
+                long v = strtol(p, &e, 10);
+                if (e == p || v < 0) { fprintf(stderr, "dogeray-b200: --devices wants a comma-separated list of device numbers\n"); return 2; }
+                devices.push_back((int)v);
+                p = (*e == ',') ? e + 1 : e;
+                if (*e && *e != ',') { fprintf(stderr, "dogeray-b200: --devices wants a comma-separated list of device numbers\n"); return 2; }
+            }
+            if (devices.empty()) { fprintf(stderr, "dogeray-b200: --devices wants at least one device\n"); return 2; }
+        }
         else if (a == "--out") out_path = next("--out");
         else if (a == "--snapshot-every") snapshot_every = atoi(next("--snapshot-every"));
         else if (a == "--save-acc") save_acc = next("--save-acc");
@@ -48,8 +67,10 @@ int main(int argc, char** argv)
         else if (a == "--cache") use_cache = true;
         else if (a == "--res") { if (sscanf(next("--res"), "%dx%d", &w, &h) != 2) { fprintf(stderr, "dogeray-b200: --res wants WxH\n"); return 2; } }
         else if (a == "-h" || a == "--help") {
-            printf("usage: dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]\n"
+            printf("usage: dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K | --gpus N | --devices a,b,..]\n"
+                   "                    [--out file.bmp|file.ppm]\n"
                    "                    [--snapshot-every N] [--save-acc file.acc] [--resume file.acc] [--cache]\n"
+                   "  --gpus / --devices  one frame over several GPUs from this process (interleaved tiles, same image as one GPU)\n"
                    "  --cache  keep the parsed scene in <scene>.drbcache (keyed by a hash of the text) and reuse it\n");
             return 0;
         } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "dogeray-b200: unknown option %s\n", a.c_str()); return 2; }
@@ -63,9 +84,13 @@ int main(int argc, char** argv)
     if (use_cache) printf("scene cache: %s\n", cache_hit ? "hit" : "miss (written)");
     printf("%lld tris\n%d textures total\n", (long long)drb_host_scene_num_objects(hs), drb_host_scene_num_textures(hs));
     if (drb_host_scene_num_skipped(hs)) fprintf(stderr, "dogeray-b200: warning: %s\n", drb_last_error());
-    drb_scene* scene = nullptr;
+    if (devices.empty()) devices.push_back(device);
+    std::vector<drb_scene*> scenes(devices.size(), nullptr);
     printf("Building BVH..\n");
-    if (drb_scene_create(hs, device, &scene) != DRB_OK) return fail("cannot create device scene");
+    for (size_t k = 0; k < devices.size(); ++k)
+        if (drb_scene_create(hs, devices[k], &scenes[k]) != DRB_OK) return fail("cannot create device scene");
+    drb_scene* scene = scenes[0];
+    if (scenes.size() > 1) printf("%zu device scenes (interleaved tile sharding)\n", scenes.size());
     drb_build_info bi;
     drb_scene_build_info(scene, &bi);
     printf("Done! %lld nodes total (upload %.2f ms, build %.2f ms)\n", (long long)bi.nnodes, bi.upload_ms, bi.build_ms);
@@ -111,7 +136,7 @@ int main(int argc, char** argv)
         opts.sample_count = total - done < chunk ? total - done : chunk;
         opts.flags = DRB_FLAG_ACCUMULATE;
         drb_stats stats;
-        if (drb_render(scene, &st, &opts, accum.data(), &stats) != DRB_OK) return fail("render failed");
+        if (drb_render_multi(scenes.data(), (int)scenes.size(), &st, &opts, accum.data(), &stats) != DRB_OK) return fail("render failed");
         have += opts.sample_count; ms_total += stats.total_ms; rays_total += stats.rays;
         if (write_image(have) != DRB_OK) return fail("cannot write image");
         if (snapshot_every > 0) printf("%llu samples -> %s\n", (unsigned long long)have, out_path.c_str());
@@ -129,7 +154,7 @@ int main(int argc, char** argv)
         }
     }
     printf("exported image:%s\n", out_path.c_str());
-    drb_scene_free(scene);
+    for (drb_scene* sc : scenes) drb_scene_free(sc);
     drb_host_scene_free(hs);
     return 0;
 }

@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -625,14 +626,16 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, const float4* _
     if (gtile % fp.tile_count != fp.tile_rank) return;                              // another shard's pixel: left untouched
     const uint32_t tile = gtile / fp.tile_count;
     const uint32_t lane = (uint32_t)((y & 3) * 8 + (x & 7));
-    f3 sum = mk3(0.f);
+    // One running sum per pixel, continued from what is already there: the value depends on the sample range only,
+    // not on how it was cut into wavefront batches, progressive chunks or tile shards (0 + c is c, so a fresh frame
+    // is the plain left-to-right sum of the reference).
+    float* dst = accum + ((size_t)y * fp.W + x) * 3;
+    f3 sum = accumulate ? mk3(dst[0], dst[1], dst[2]) : mk3(0.f);
     for (uint32_t s = 0; s < fp.samples; ++s) {
         const float4 c = contrib[(size_t)(tile * fp.samples + s) * 32u + lane];
         sum = sum + mk3(c.x, c.y, c.z);                              // ColorOutput += raycolor(...), kernel.cu:1076
     }
-    float* dst = accum + ((size_t)y * fp.W + x) * 3;
-    if (accumulate) { dst[0] += sum.x; dst[1] += sum.y; dst[2] += sum.z; }
-    else { dst[0] = sum.x; dst[1] = sum.y; dst[2] = sum.z; }
+    dst[0] = sum.x; dst[1] = sum.y; dst[2] = sum.z;
 }
 
 // rays of explicit (o, d) arrays -> queue 0
@@ -1015,6 +1018,60 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
     if (int rc = render_core(s, settings, &o, settings->width, settings->height, 1, d, stats)) return rc;
     DRB_CUDA(cudaMemcpyAsync(accum_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
     DRB_CUDA(cudaStreamSynchronize(stream));
+    return DRB_OK;
+}
+
+int drb_render_multi(drb_scene* const* scenes, int nscenes, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats)
+{
+    if (!scenes || nscenes < 1 || !accum_host) { drb_set_error("drb_render_multi: bad argument"); return DRB_ERR_ARG; }
+    for (int k = 0; k < nscenes; ++k)
+        if (!scenes[k]) { drb_set_error("drb_render_multi: scene %d is null", k); return DRB_ERR_ARG; }
+    if (int rc = check_settings(settings)) return rc;
+    drb_opts base; if (opts) base = *opts; else drb_opts_default(&base);
+    if (base.stream) { drb_set_error("drb_render_multi: opts->stream must be NULL (each handle renders on its own stream)"); return DRB_ERR_ARG; }
+    if (nscenes == 1) { base.tile_rank = 0; base.tile_count = 1; return drb_render(scenes[0], settings, &base, accum_host, stats); }
+    const int W = settings->width, H = settings->height;
+    const size_t n = (size_t)W * H * 3;
+    // Every shard starts from the caller's image and changes only its own tiles, so picking each pixel from the
+    // shard that owns it reproduces the one-handle result bit for bit, with or without DRB_FLAG_ACCUMULATE.
+    std::vector<std::vector<float>> shard((size_t)nscenes - 1);
+    std::vector<int> rcs((size_t)nscenes, DRB_OK);
+    std::vector<std::string> errs((size_t)nscenes);
+    std::vector<drb_stats> sts((size_t)nscenes);
+    auto work = [&](int k, float* dst) {
+        drb_opts o = base;
+        o.tile_rank = (uint32_t)k; o.tile_count = (uint32_t)nscenes;
+        memset(&sts[(size_t)k], 0, sizeof(drb_stats));
+        rcs[(size_t)k] = drb_render(scenes[k], settings, &o, dst, &sts[(size_t)k]);
+        if (rcs[(size_t)k] != DRB_OK) errs[(size_t)k] = drb_last_error();       // the message is thread-local
+    };
+    std::vector<std::thread> pool;
+    for (int k = 1; k < nscenes; ++k) {
+        shard[(size_t)k - 1].assign(accum_host, accum_host + n);
+        pool.emplace_back(work, k, shard[(size_t)k - 1].data());
+    }
+    work(0, accum_host);                                                        // shard 0 renders in place
+    for (auto& th : pool) th.join();
+    for (int k = 0; k < nscenes; ++k)
+        if (rcs[(size_t)k] != DRB_OK) { drb_set_error("drb_render_multi: scene %d: %s", k, errs[(size_t)k].c_str()); return rcs[(size_t)k]; }
+    const int tiles_x = (W + 7) / 8;
+    for (int y = 0; y < H; ++y)
+        for (int tx = 0; tx < tiles_x; ++tx) {
+            const uint32_t owner = ((uint32_t)(y >> 2) * (uint32_t)tiles_x + (uint32_t)tx) % (uint32_t)nscenes;
+            if (owner == 0) continue;
+            const size_t at = ((size_t)y * W + (size_t)tx * 8) * 3;
+            const size_t len = (size_t)std::min(8, W - tx * 8) * 3;
+            memcpy(accum_host + at, shard[owner - 1].data() + at, len * sizeof(float));
+        }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (const drb_stats& t : sts) {
+            stats->paths += t.paths; stats->rays += t.rays;
+            stats->trace_launches += t.trace_launches; stats->kernel_launches += t.kernel_launches;
+            stats->trace_ms = std::max(stats->trace_ms, t.trace_ms);            // the handles run side by side
+            stats->total_ms = std::max(stats->total_ms, t.total_ms);
+        }
+    }
     return DRB_OK;
 }
 

@@ -850,7 +850,7 @@ int drb_scene_create_ex(const drb_host_scene* hs, int device, uint32_t build_fla
     if (int prc = retain_pool(device)) { cudaStreamDestroy(s->stream); delete s; return prc; }
     // page-lock the object lines once per host scene so the upload runs at PCIe speed (and again for free next frame)
     if (!hs->objects.empty() && !hs->pinned) {
-        if (cudaHostRegister((void*)hs->objects.data(), hs->objects.size() * sizeof(drb_object), cudaHostRegisterDefault) == cudaSuccess) hs->pinned = true;
+        if (cudaHostRegister((void*)hs->objects.data(), hs->objects.size() * sizeof(drb_object), cudaHostRegisterPortable) == cudaSuccess) hs->pinned = true;
         else cudaGetLastError();
     }
     int rc = upload_textures(s, hs);

@@ -194,6 +194,14 @@ void drb_opts_default(drb_opts* out);
 int drb_render_device(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_dev, drb_stats* stats);
 /* Same with a HOST accumulation buffer (synchronous; includes the device->host copy). */
 int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats);
+/* One frame over several resident scenes -- normally the same scene created on different devices (SURVEY.md
+ * 8(b)3 "device list", 8(e)) -- from one process: one host thread per handle, handle k traces the 8x4-pixel tiles t
+ * with t % nscenes == k (opts->tile_rank / tile_count are overridden), and the shards are merged on the host.
+ * Pixel sets are disjoint, so the image is bit-identical to drb_render on a single handle, with or without
+ * DRB_FLAG_ACCUMULATE.  opts->stream must be NULL.  `stats`: paths, rays and launches are summed, times are the
+ * maximum over handles.  (torch.distributed callers use drb_render_device + one reduce instead) */
+int drb_render_multi(drb_scene* const* scenes, int nscenes, const drb_settings* settings, const drb_opts* opts,
+                     float* accum_host, drb_stats* stats);
 
 /* Exact output contract of CudaStarter (kernel.cu:2562-2669, Kernel :998-1093): out[(x*H + y)*3 + c] =
  * trunc(255 * mean radiance) for x < W/divisor/8*8, y < H/divisor/8*8, other entries untouched.

@@ -62,3 +62,15 @@ def test_error_codes():
     with pytest.raises(drb.DogerayError) as e:
         drb.read_ppm("/nonexistent.ppm")
     assert e.value.status == drb.ERR_IO
+
+
+def test_render_multi_rejects_bad_arguments_before_touching_cuda():
+    import ctypes as C
+    st = drb.Settings(); drb._lib.drb_settings_default(C.byref(st))
+    buf = (C.c_float * (st.width * st.height * 3))()
+    none = (C.c_void_p * 2)(None, None)
+    assert drb._lib.drb_render_multi(none, 0, C.byref(st), None, buf, None) == drb.ERR_ARG
+    assert drb._lib.drb_render_multi(None, 2, C.byref(st), None, buf, None) == drb.ERR_ARG
+    assert drb._lib.drb_render_multi(none, 2, C.byref(st), None, buf, None) == drb.ERR_ARG and b"scene 0 is null" in drb._lib.drb_last_error()
+    assert drb._lib.drb_render_multi(none, 2, C.byref(st), None, None, None) == drb.ERR_ARG
+

@@ -80,4 +80,23 @@ def test_cli_progressive_snapshots_and_resume(tmp_path):
     full = np.frombuffer(open(tmp_path / "full.ppm", "rb").read()[len(b"P6\n48 32\n255\n"):], np.uint8).astype(int)
     for name in ("prog.ppm", "b.ppm"):
         img = np.frombuffer(open(tmp_path / name, "rb").read()[len(b"P6\n48 32\n255\n"):], np.uint8).astype(int)
-        assert np.abs(img - full).max() <= 1                      # float sums in another association: at most one 8-bit step
+        assert np.array_equal(img, full)                          # chunks and resumes continue one running sum per pixel
+
+
+@pytest.mark.gpu
+def test_cli_device_list_renders_the_one_gpu_image(tmp_path):
+    """--devices 0,0,0: three device scenes, three host threads, interleaved tiles -> byte-identical BMP"""
+    objs, st = synth.heightfield_scene(n=12, width=52, height=30, spp=4, max_depth=4)
+    drb.write_rts(str(tmp_path / "s.rts"), st, objs)
+    run = lambda *a: subprocess.run([CLI, "s.rts", "--seed", "6"] + list(a), capture_output=True, text=True, cwd=tmp_path)
+    p = run("--out", "one.bmp"); assert p.returncode == 0, p.stdout + p.stderr
+    p = run("--devices", "0,0,0", "--out", "three.bmp"); assert p.returncode == 0, p.stdout + p.stderr
+    assert "3 device scenes" in p.stdout
+    assert open(tmp_path / "one.bmp", "rb").read() == open(tmp_path / "three.bmp", "rb").read()
+    # progressive chunks, one handle or two: the float accumulators themselves are identical
+    p = run("--gpus", "1", "--snapshot-every", "2", "--out", "prog1.ppm", "--save-acc", "p1.acc"); assert p.returncode == 0, p.stdout + p.stderr
+    p = run("--devices", "0,0", "--snapshot-every", "2", "--out", "prog2.ppm", "--save-acc", "p2.acc"); assert p.returncode == 0, p.stdout + p.stderr
+    assert open(tmp_path / "p1.acc", "rb").read() == open(tmp_path / "p2.acc", "rb").read()            # the float accumulators
+    assert open(tmp_path / "prog1.ppm", "rb").read() == open(tmp_path / "prog2.ppm", "rb").read()
+    p = run("--devices", "0,99"); assert p.returncode == 1 and "cannot create device scene" in p.stderr
+

@@ -176,13 +176,13 @@ def test_render_properties_batches_shards_accumulate():
     again, _ = sc.render(st, seed=4)
     assert np.array_equal(full, again)                                       # deterministic
     small, s_small = sc.render(st, seed=4, batch_paths=64 * 40 * 2)          # 4 wavefront batches instead of 1
-    assert s_small.rays == s_full.rays and np.allclose(small, full, rtol=0, atol=2e-5)
+    assert s_small.rays == s_full.rays and np.array_equal(small, full)       # one running sum per pixel: batching does not show
     a, sa = sc.render(st, seed=4, sample_base=0, sample_count=3)             # two sample shards ...
     b, sb = sc.render(st, seed=4, sample_base=3, sample_count=5)
     assert sa.rays + sb.rays == s_full.rays and np.allclose(a + b, full, rtol=0, atol=2e-5)
     acc = a.copy()
     acc, _ = sc.render(st, seed=4, sample_base=3, sample_count=5, accumulate_into=acc)   # ... or accumulated in place
-    assert np.allclose(acc, full, rtol=0, atol=2e-5)
+    assert np.array_equal(acc, full)                                         # ... which continues the same running sum
     other, _ = sc.render(st, seed=5)
     assert not np.array_equal(other, full)
 
@@ -425,3 +425,44 @@ def test_tile_sharding_is_bit_identical_to_the_whole_image():
     assert np.array_equal(parts[0] + parts[1] + parts[2], full)                                        # bit-identical
     with pytest.raises(drb.DogerayError):
         sc.render(st, tile_rank=3, tile_count=3)
+
+
+def test_render_multi_over_several_handles_is_bit_identical_to_one_handle():
+    """drb_render_multi: one host thread per handle, interleaved tiles, merged on the host.  Two and three handles on
+    device 0 stand in for two and three GPUs (the code path is the same; only the device number differs)."""
+    objs, st = synth.heightfield_scene(n=24, width=83, height=47, spp=6, max_depth=5)      # ragged right and bottom tiles
+    hs = drb.HostScene.from_objects(objs, st)
+    scenes = [drb.Scene.from_host(hs) for _ in range(3)]
+    full, sf = scenes[0].render(st, seed=21)
+    for n in (1, 2, 3):
+        img, sm = drb.render_multi(scenes[:n], st, seed=21)
+        assert np.array_equal(img, full), n
+        assert sm.rays == sf.rays and sm.paths == sf.paths == 83 * 47 * 6
+        assert sm.kernel_launches >= sf.kernel_launches
+    # accumulate: two half-frames over two handles == the two half-frames on one handle
+    a, _ = scenes[0].render(st, seed=21, sample_base=0, sample_count=3)
+    a, _ = scenes[0].render(st, seed=21, sample_base=3, sample_count=3, accumulate_into=a)
+    b, _ = drb.render_multi(scenes[:2], st, seed=21, sample_base=0, sample_count=3)
+    b, _ = drb.render_multi(scenes[:2], st, seed=21, sample_base=3, sample_count=3, accumulate_into=b)
+    assert np.array_equal(a, b)
+    # small batches inside every shard
+    c, _ = drb.render_multi(scenes, st, seed=21, batch_paths=4096)
+    assert np.array_equal(c, full)
+    with pytest.raises(drb.DogerayError):
+        bad = drb.Settings.from_buffer_copy(bytes(st)); bad.width = 0
+        drb.render_multi(scenes[:2], bad)
+
+
+def test_render_multi_on_two_devices():
+    """the same through real peers: the scene created on device 0 and on device 1"""
+    if drb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    objs, st = synth.heightfield_scene(n=32, width=130, height=75, spp=8, max_depth=6)
+    hs = drb.HostScene.from_objects(objs, st)
+    s0, s1 = drb.Scene.from_host(hs, device=0), drb.Scene.from_host(hs, device=1)
+    full, sf = s0.render(st, seed=5)
+    other, _ = s1.render(st, seed=5)
+    assert np.array_equal(full, other)                                     # the build and the frame do not depend on the device
+    img, sm = drb.render_multi([s0, s1], st, seed=5)
+    assert np.array_equal(img, full) and sm.rays == sf.rays
+
