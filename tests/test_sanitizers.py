@@ -55,3 +55,21 @@ def test_loader_cache_and_writer_are_clean_on_written_scenes(harness, tmp_path):
 def test_loader_cache_and_writer_are_clean_on_every_shipped_scene(harness, tmp_path):
     files = sorted(os.path.join(SAMPLES, n) for n in os.listdir(SAMPLES) if n.endswith(".rts"))
     run(harness, tmp_path, files)
+
+
+def test_threaded_parse_hash_and_writer_are_race_free(tmp_path):
+    """ThreadSanitizer over the parallel paths: line-range parse threads, chunk hash threads, the writer's workers"""
+    out = str(tmp_path / "tsan_host")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+           os.path.join(ROOT, "tests", "native", "sanitize_host_main.cpp"), os.path.join(CSRC, "rts_loader.cpp"),
+           os.path.join(CSRC, "image_io.cpp"), "-o", out, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("tsan runtime not available: " + r.stderr[-300:])
+    objs, st = synth.heightfield_scene(200, seed=1)                     # 80 000 triangles, 26 MB of text: every pool is used
+    p = str(tmp_path / "t.rts")
+    drb.write_rts(p, st, objs)
+    r = subprocess.run([out, p], capture_output=True, text=True, env=dict(os.environ, DRB_SAN_TMP=str(tmp_path)), timeout=600)
+    if "unexpected memory mapping" in r.stderr:
+        pytest.skip("tsan cannot run in this container")
+    assert r.returncode == 0 and "bad 0" in r.stdout and "WARNING: ThreadSanitizer" not in r.stderr, (r.stdout + r.stderr)[-3000:]
