@@ -102,6 +102,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows = []
+        self.first = 0
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
@@ -115,6 +116,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """the timed region starts here: earlier rows (the sampler's own start-up, the warm-up steps) do not count"""
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -125,7 +130,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:] or self.rows[-1:]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -344,15 +349,20 @@ def main():
             dist.reduce(accum, dst=0)
         return s
 
+    # nvidia-smi is started BEFORE the warm-up: its NVML start-up holds driver locks for tens of milliseconds, which
+    # showed up as a ~85 ms hole in the kernel launches of the first timed step when it was started after it
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(W):
         step_resident()
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = 0; paths = 0; trace_ms = 0.0; launches = 0; trace_launches = 0
     e0.record()
     for _ in range(K):
         s = step_resident()
+        log("[rank %d] resident step: %.1f ms total, %.1f ms in k_trace" % (rank, s.total_ms, s.trace_ms))
         rays += s.rays; paths += s.paths; trace_ms += s.trace_ms; launches += s.kernel_launches; trace_launches += s.trace_launches
     e1.record()
     barrier()
@@ -393,6 +403,7 @@ def main():
         t4 = time.perf_counter()
         for k, v in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             e2e_parts[k] += v * 1e3
+        log("[rank %d] e2e step: create %.1f ms, render %.1f ms (device %.1f, k_trace %.1f)" % (rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, s.total_ms, s.trace_ms))
         return s
 
     scene.close()

@@ -60,5 +60,23 @@ struct PathRng {
         if (lane == 0u) refill(n >> 2);
         return lane == 0u ? w0 : (lane == 1u ? w1 : (lane == 2u ? w2 : w3));
     }
-    DRB_HD float uniform() { return ((float)(word() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+    static DRB_HD float to_uniform(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+    DRB_HD float uniform() { return to_uniform(word()); }
+    // The next three words at once (draws n, n+1, n+2).  Same stream as three word() calls, but the block function
+    // sits at ONE call site: lanes of a warp whose streams are at different phases (n & 3) generate their next block
+    // together instead of one phase after the other, which is what three word() calls compile to.
+    DRB_HD void words3(uint32_t& a, uint32_t& b, uint32_t& c)
+    {
+        const uint32_t ph = draws & 3u;
+        uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        if (ph != 1u) {                                   // phase 1 still holds w1 w2 w3
+            Philox4 p = philox4x32_10(k0, k1, x, y, sample, (draws + 3u) >> 2);
+            n0 = p.v[0]; n1 = p.v[1]; n2 = p.v[2]; n3 = p.v[3];
+        }
+        a = ph == 0u ? n0 : (ph == 1u ? w1 : (ph == 2u ? w2 : w3));
+        b = ph == 0u ? n1 : (ph == 1u ? w2 : (ph == 2u ? w3 : n0));
+        c = ph == 0u ? n2 : (ph == 1u ? w3 : (ph == 2u ? n0 : n1));
+        if (ph != 1u) { w0 = n0; w1 = n1; w2 = n2; w3 = n3; }
+        draws += 3u;
+    }
 };

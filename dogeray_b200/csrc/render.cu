@@ -27,7 +27,9 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -108,7 +110,9 @@ DRB_D bool slot_to_pixel(const FrameParams& fp, uint32_t slot, int& x, int& y, u
 DRB_D f3 random_in_unit_sphere(PathRng& rng)
 {
     for (;;) {
-        const float c = rng.uniform(), b = rng.uniform(), a = rng.uniform();
+        uint32_t wc, wb, wa;
+        rng.words3(wc, wb, wa);
+        const float c = PathRng::to_uniform(wc), b = PathRng::to_uniform(wb), a = PathRng::to_uniform(wa);
         const f3 p = mk3(a * 2.0f - 1.0f, b * 2.0f - 1.0f, c * 2.0f - 1.0f);
         const float l = length(p);
         if (l * l >= 1.0f) continue;
@@ -509,32 +513,28 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Q
 
                     f3 ndir = raydir;
                     alive = true;
-                    if (mat == 0) {
-                        // diffuse, kernel.cu:848-866
+                    // Every lobe that needs a point in the unit sphere draws it here, at one call site, so that the
+                    // diffuse, metal and glossy lanes of a warp run their rejection loops together.  Draw order per
+                    // path is the reference's: glossy picks its lobe first (kernel.cu:885), then samples.
+                    const float pick = mat == 5 ? rng.uniform() : 0.0f;
+                    const bool metal_lobe = mat == 3 || (mat == 5 && pick > 0.8f);
+                    const bool diffuse_lobe = mat == 0 || (mat == 5 && !(pick > 0.8f));
+                    f3 rs = mk3(0.f);
+                    if (metal_lobe || diffuse_lobe) rs = random_in_unit_sphere(rng);
+                    if (diffuse_lobe) {
+                        // diffuse, kernel.cu:848-866; the diffuse lobe of glossy (:900-910) never normalises the sample
                         f3 target = hitpoint + N;
-                        if (r2.x == 0.0f) target = target + random_in_unit_sphere(rng);
-                        else target = target + normalize(random_in_unit_sphere(rng));
+                        if (mat == 5 || r2.x == 0.0f) target = target + rs;
+                        else target = target + normalize(rs);
                         atten = atten * ocolor;
                         ndir = normalize(target - hitpoint);
+                    } else if (metal_lobe) {
+                        const f3 reflected = reflect(normalize(raydir), N);     // metal, kernel.cu:875-883; glossy :886-898
+                        atten = atten * ocolor;
+                        ndir = reflected + mk3(rough) * rs;
                     } else if (mat == 2) {
                         atten = atten * ocolor;                                 // mirror, kernel.cu:867-874
                         ndir = reflect(normalize(raydir), N);
-                    } else if (mat == 3) {
-                        const f3 reflected = reflect(normalize(raydir), N);     // metal, kernel.cu:875-883
-                        atten = atten * ocolor;
-                        ndir = reflected + mk3(rough) * random_in_unit_sphere(rng);
-                    } else if (mat == 5) {
-                        const float pick = rng.uniform();                       // glossy, kernel.cu:884-912
-                        if (pick > 0.8f) {
-                            const f3 reflected = reflect(normalize(raydir), N);
-                            atten = atten * ocolor;
-                            ndir = reflected + mk3(rough) * random_in_unit_sphere(rng);
-                        } else {
-                            f3 target = hitpoint + N;
-                            target = target + random_in_unit_sphere(rng);
-                            atten = atten * ocolor;
-                            ndir = normalize(target - hitpoint);
-                        }
                     } else if (mat == 4) {
                         // glass, kernel.cu:914-939 (ior comes from addional.y even when a roughness map is bound)
                         const float ir = r1.w;
@@ -778,6 +778,9 @@ int ensure_buffers(drb_scene* s, size_t slots)
                                                  (int)std::min<size_t>(slots, 0x7FFFFFFF), 0, 24, st));
         DRB_CUDA(drb_dev_alloc(&rb->sort_tmp, rb->sort_tmp_bytes ? rb->sort_tmp_bytes : 16, st));
     }
+    if (getenv("DOGERAY_B200_DEBUG"))
+        fprintf(stderr, "[dogeray_b200] queues for %zu slots: o %p %p d %p %p thr %p %p hit %p contrib %p\n", slots, (void*)q.ray_o[0], (void*)q.ray_o[1],
+                (void*)q.ray_d[0], (void*)q.ray_d[1], (void*)q.thr[0], (void*)q.thr[1], (void*)q.hit, (void*)q.contrib);
     DRB_CUDA(cudaMemsetAsync(q.counters, 0, CNT_WORDS * sizeof(uint32_t), st));
     DRB_CUDA(cudaStreamSynchronize(st));             // the buffers may be used from a caller-provided stream next
     rb->capacity = slots;
@@ -847,6 +850,7 @@ struct EventPool {
 // the wavefront loop for a W x H grid; accum is a device buffer of W*H*3 floats
 int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int W, int H, int divisor, float* accum, drb_stats* stats)
 {
+    const auto t_enter = std::chrono::steady_clock::now();
     drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
     const uint32_t total_samples = o.sample_count ? o.sample_count : (uint32_t)std::max(st->spp, 0);
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
@@ -866,8 +870,13 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
     size_t want = o.batch_paths;
     if (!want) {
         want = (size_t)128 << 20;
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::max<size_t>(std::min(want, (size_t)(0.25 * (double)total_b) / 120), (size_t)1 << 20);
+        // asked once per handle: the driver call takes a device-wide lock and was seen to stall for tens of
+        // milliseconds when a monitoring process polls the GPU at the same time
+        if (!s->device_mem) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->device_mem = total_b; else cudaGetLastError();
+        }
+        if (s->device_mem) want = std::max<size_t>(std::min(want, (size_t)(0.25 * (double)s->device_mem) / 120), (size_t)1 << 20);
     }
     uint32_t per_batch = 1;
     for (;;) {
@@ -890,6 +899,8 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
     fp.cam = make_camera(*st, st->width, st->height, divisor);     // aspect and u/v denominators come from the FULL size
     const DevScene sc = dev_scene(s);
 
+    const bool debug = getenv("DOGERAY_B200_DEBUG") != nullptr;
+    const auto t_setup = std::chrono::steady_clock::now();
     EventPool pool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_ev;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -944,6 +955,11 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
         launches += 1;
     }
     DRB_CUDA(cudaGetLastError());
+    if (debug) {
+        const double setup_ms = std::chrono::duration<double, std::milli>(t_setup - t_enter).count();
+        const double loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup).count();
+        fprintf(stderr, "[dogeray_b200] render_core host time: setup %.2f ms, launch loop %.2f ms\n", setup_ms, loop_ms);
+    }
     if (stats) {
         DRB_CUDA(cudaEventRecord(ev_end, stream));
         uint64_t rays = 0;
