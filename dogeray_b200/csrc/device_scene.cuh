@@ -121,7 +121,6 @@ struct drb_scene {
     cudaStream_t stream = nullptr;
     // render work buffers, grown on demand (render.cu)
     struct RenderBuffers* rb = nullptr;
-    size_t device_mem = 0;                  // total device memory, asked once (render.cu sizes its batches from it)
 };
 
 #define DRB_CUDA(call)                                                                                     \

@@ -32,6 +32,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -752,6 +754,51 @@ Camera make_camera(const drb_settings& st, int W, int H, int divisor)
 // on B200 the sort costs more than the ~5 % of traversal time it saves on the 1 M-triangle workload)
 long g_sort_min = []() { const char* e = getenv("DOGERAY_B200_SORT_MIN"); return e ? atol(e) : 0L; }();
 
+// Grid sizes of the persistent kernels and the total device memory are properties of the device: they are asked
+// once per process and device (and per stack size), not once per scene handle.  Each of these driver calls takes a
+// device-wide lock; with a new handle every frame (the CudaStarter pattern) they were seen to stall a frame for
+// tens of milliseconds whenever a monitoring process polled the GPU at the same moment.
+struct DeviceFacts {
+    std::mutex mu;
+    size_t total_mem[64] = { 0 };
+    int shade_blocks[64] = { 0 };
+    std::map<std::pair<int, size_t>, int> trace_blocks;        // (device, dynamic smem) -> grid
+    size_t max_smem_set[64] = { 0 };
+} g_facts;
+
+int launch_shape(int device, size_t trace_smem, int* trace_blocks, int* shade_blocks)
+{
+    std::lock_guard<std::mutex> g(g_facts.mu);
+    const int d = device & 63;
+    auto it = g_facts.trace_blocks.find({ device, trace_smem });
+    if (it == g_facts.trace_blocks.end() || !g_facts.shade_blocks[d]) {
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (trace_smem > g_facts.max_smem_set[d]) {
+            DRB_CUDA(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
+            g_facts.max_smem_set[d] = trace_smem;
+        }
+        DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, kTraceThreads, trace_smem));
+        it = g_facts.trace_blocks.emplace(std::make_pair(device, trace_smem), sms * std::max(per_sm, 1)).first;
+        DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 128, 0));
+        g_facts.shade_blocks[d] = sms * std::max(per_sm, 1);
+    }
+    *trace_blocks = it->second;
+    *shade_blocks = g_facts.shade_blocks[d];
+    return DRB_OK;
+}
+
+size_t device_total_mem(int device)
+{
+    std::lock_guard<std::mutex> g(g_facts.mu);
+    size_t& t = g_facts.total_mem[device & 63];
+    if (!t) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) t = total_b; else cudaGetLastError();
+    }
+    return t;
+}
+
 int ensure_buffers(drb_scene* s, size_t slots)
 {
     if (!s->rb) s->rb = new RenderBuffers();
@@ -784,16 +831,9 @@ int ensure_buffers(drb_scene* s, size_t slots)
     DRB_CUDA(cudaMemsetAsync(q.counters, 0, CNT_WORDS * sizeof(uint32_t), st));
     DRB_CUDA(cudaStreamSynchronize(st));             // the buffers may be used from a caller-provided stream next
     rb->capacity = slots;
-    int sms = 148, per_sm = 1;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
     // worst case three pushes per level of the four-wide tree, plus the sentinel
     rb->trace_smem = (size_t)(3 * std::max(s->wide_levels, 1) + 2) * kTraceThreads * sizeof(int);
-    DRB_CUDA(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb->trace_smem));
-    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, kTraceThreads, rb->trace_smem));
-    rb->trace_blocks = sms * std::max(per_sm, 1);
-    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 128, 0));
-    rb->shade_blocks = sms * std::max(per_sm, 1);
-    return DRB_OK;
+    return launch_shape(s->device, rb->trace_smem, &rb->trace_blocks, &rb->shade_blocks);
 }
 
 DevScene dev_scene(const drb_scene* s)
@@ -870,13 +910,8 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
     size_t want = o.batch_paths;
     if (!want) {
         want = (size_t)128 << 20;
-        // asked once per handle: the driver call takes a device-wide lock and was seen to stall for tens of
-        // milliseconds when a monitoring process polls the GPU at the same time
-        if (!s->device_mem) {
-            size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->device_mem = total_b; else cudaGetLastError();
-        }
-        if (s->device_mem) want = std::max<size_t>(std::min(want, (size_t)(0.25 * (double)s->device_mem) / 120), (size_t)1 << 20);
+        const size_t device_mem = device_total_mem(s->device);
+        if (device_mem) want = std::max<size_t>(std::min(want, (size_t)(0.25 * (double)device_mem) / 120), (size_t)1 << 20);
     }
     uint32_t per_batch = 1;
     for (;;) {
