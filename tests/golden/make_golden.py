@@ -8,6 +8,9 @@ Vectors (all small, committed):
                          the product's .rts writer, loaded by the reference's read()): primary rays, closest-hit
                          ids / t from the reference's hit(), and a 48x40 float frame from the reference's Kernel()
   cube_frame.npz         samples/cube.rts, camera (6,-5,9), 40x32, 3 spp, depth 4, seed 11: ids / t / float frame
+  synth_materials.npz    dogeray_b200.synth.materials_scene at 24x12 per blob (every material class of the reference,
+                         colour + roughness textures, checker, smooth normals, environment map; textures from
+                         synth.write_test_textures), 96x56, 3 spp, depth 6, seed 13: ids / t / float frame
   philox_kat.json        Random123 known-answer vectors for Philox4x32-10 (published with the algorithm)
 """
 import json
@@ -52,6 +55,13 @@ def main():
         golden_for(ref, p, "", st, 5, os.path.join(HERE, "synth_heightfield.npz"))
     st = drb.HostScene.load(os.path.join(refhost.SAMPLES, "cube.rts")).settings.replace(cam=(6.0, -5.0, 9.0), width=40, height=32, spp=3, max_depth=4)
     golden_for(ref, os.path.join(refhost.SAMPLES, "cube.rts"), "", st, 11, os.path.join(HERE, "cube_frame.npz"))
+    with tempfile.TemporaryDirectory() as td:
+        tex = synth.write_test_textures(td)
+        objs, st, tp = synth.materials_scene(tex, width=96, height=56, spp=3, max_depth=6, nu=24, nv=12)
+        p = os.path.join(td, "mats.rts")
+        drb.write_rts(p, st, objs, tex_names=[os.path.basename(t) for t in tp], backtex_name=os.path.basename(tp[0]))
+        st = drb.HostScene.load(p, td).settings                      # backtex resolved against the directory
+        golden_for(ref, p, td, st, 13, os.path.join(HERE, "synth_materials.npz"))
     kat = [
         {"ctr": [0, 0, 0, 0], "key": [0, 0], "out": [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]},
         {"ctr": [0xffffffff] * 4, "key": [0xffffffff] * 2, "out": [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]},

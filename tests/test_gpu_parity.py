@@ -123,6 +123,26 @@ def test_golden_synthetic_scene(tmp_path):
     assert np.array_equal(sc.frame_i3(st, 1, seed=int(g["seed"])), g["frame_i"])
 
 
+def test_golden_materials_scene(tmp_path):
+    """BASELINE config 4 in small against numbers that came from the reference: no oracle needed at run time"""
+    g = np.load(os.path.join(GOLDEN, "synth_materials.npz"))
+    tex = synth.write_test_textures(str(tmp_path))
+    objs, st, tp = synth.materials_scene(tex, width=96, height=56, spp=3, max_depth=6, nu=24, nv=12)
+    p = str(tmp_path / "mats.rts")
+    drb.write_rts(p, st, objs, tex_names=[os.path.basename(t) for t in tp], backtex_name=os.path.basename(tp[0]))
+    sc = drb.Scene.load(p, str(tmp_path))
+    st = sc.settings
+    seed = int(g["seed"])
+    o, d = sc.primary_rays(st, sample=0, seed=seed)
+    assert np.array_equal(o, g["origins"]) and np.array_equal(d, g["dirs"])
+    ids, t = sc.trace_ids(o, d)
+    assert np.array_equal(ids, g["ids"]) and np.array_equal(t, g["t"])
+    acc, stats = sc.render(st, seed=seed)
+    assert stats.rays == int(g["rays"])
+    assert np.array_equal(acc.transpose(1, 0, 2) * np.float32(255.0) * np.float32(1.0 / 3), g["frame"])
+    assert np.array_equal(sc.frame_i3(st, 1, seed=seed), g["frame_i"])
+
+
 @needs_ref
 def test_golden_cube():
     g = np.load(os.path.join(GOLDEN, "cube_frame.npz"))

@@ -84,6 +84,18 @@ def test_restatement_against_golden_synthetic(tmp_path):
     _check_golden(g, restated.Restated(p))
 
 
+def test_restatement_against_golden_materials(tmp_path):
+    """every material class, colour + roughness textures, checker, smooth normals, environment map -- expected values
+    from the reference, scene and textures regenerated here"""
+    g = np.load(os.path.join(GOLDEN, "synth_materials.npz"))
+    tex = synth.write_test_textures(str(tmp_path))
+    objs, st, tp = synth.materials_scene(tex, width=96, height=56, spp=3, max_depth=6, nu=24, nv=12)
+    p = str(tmp_path / "mats.rts")
+    drb.write_rts(p, st, objs, tex_names=[os.path.basename(t) for t in tp], backtex_name=os.path.basename(tp[0]))
+    assert int(g["settings"][12]) == 0                                  # the environment map is texture 0
+    _check_golden(g, restated.Restated(p, str(tmp_path)))
+
+
 @needs_ref
 def test_restatement_against_golden_cube():
     g = np.load(os.path.join(GOLDEN, "cube_frame.npz"))
