@@ -164,3 +164,27 @@ def test_host_lbvh_is_a_valid_tree():
                 else:
                     assert i < ch < len(w["child"])
         assert (seen == 1).all()
+
+
+def _sah(node_min, node_max):
+    """surface-area-heuristic cost of the inner nodes, relative to the root (one-primitive leaves cost the same in
+    every tree over the same primitives, so they are left out)"""
+    e = (node_max - node_min).astype(np.float64)
+    a = e[:, 0] * e[:, 1] + e[:, 1] * e[:, 2] + e[:, 2] * e[:, 0]
+    return float(a.sum() / a[0])
+
+
+def test_sah_guided_rebuild_beats_the_morton_tree():
+    """regression guard on tree quality (the GPU build is bit-identical to these mirrors, tests/test_gpu_parity.py):
+    on a mesh-like scene the rebuilt tree has a clearly lower SAH cost than the Karras tree over the same order"""
+    objs, st = synth.heightfield_scene(n=60)                               # 7 200 triangles
+    tri = objs[objs["type"] == 2]
+    v = np.stack([tri["pos"], tri["dim"], tri["rot"]], 1).astype(np.float32)
+    bmin, bmax = v.min(1), v.max(1)
+    t = restated.lbvh_host(bmin, bmax)
+    lmin, lmax = bmin[t["order"]], bmax[t["order"]]
+    morton = _sah(t["node_min"], t["node_max"])
+    costs = {r: _sah(*(lambda p: (p["node_min"], p["node_max"]))(restated.ploc_host(lmin, lmax, radius=r))) for r in (1, 4, 16, 64)}
+    assert costs[16] < 0.80 * morton, (morton, costs)
+    assert costs[16] <= costs[4] <= costs[1] * 1.001, costs               # a wider search never hurts on this scene
+    assert costs[64] > 0.97 * costs[16], costs                            # ... and radius 16 already has nearly all of it
