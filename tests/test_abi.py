@@ -74,3 +74,34 @@ def test_render_multi_rejects_bad_arguments_before_touching_cuda():
     assert drb._lib.drb_render_multi(none, 2, C.byref(st), None, buf, None) == drb.ERR_ARG and b"scene 0 is null" in drb._lib.drb_last_error()
     assert drb._lib.drb_render_multi(none, 2, C.byref(st), None, None, None) == drb.ERR_ARG
 
+
+
+def _build_c_consumer(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_consumer")
+    libdir = os.path.dirname(drb.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "native", "abi_consumer.c"), "-o", exe, "-L" + libdir, "-ldogeray_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr                                   # the header is valid, warning-free C99
+    return subprocess.run([exe], capture_output=True, text=True, timeout=300)
+
+
+def test_header_is_plain_c_and_struct_sizes_agree(tmp_path):
+    r = _build_c_consumer(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sizes settings=%d object=%d opts=%d stats=%d build_info=%d abi=1" % (
+        ctypes.sizeof(drb.Settings), drb.OBJECT_DTYPE.itemsize, ctypes.sizeof(drb.Opts), ctypes.sizeof(drb.Stats), ctypes.sizeof(drb.BuildInfo)) in r.stdout
+    assert "parsed objects=2 width=16 height=8" in r.stdout
+    if drb.device_count() == 0:
+        assert "no device: drb_scene_create -> -4" in r.stdout and "no CPU path" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_consumer_renders_through_the_abi(tmp_path):
+    r = _build_c_consumer(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rendered paths=256" in r.stdout
