@@ -1,6 +1,9 @@
+"""Developer diagnostic (test infrastructure: it uses the oracle as the checker): the randomised scenes of
+tests/test_gpu_parity_wide.py one by one, printing where ids / distances / radiance differ from the host-compiled
+reference.  Run on a GPU box: python tests/dev/fuzz_diag.py"""
 import os, sys, tempfile
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dogeray_b200 as drb
 from oracle import refhost, restated

@@ -1,5 +1,8 @@
+"""Half the tiles against half the samples of the 1 M-triangle frame on one GPU (what a rank of a 2-GPU run
+traces under --shard tiles resp. --shard samples).  python tools/tile_timing.py"""
 import sys, time
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import dogeray_b200 as drb
 from dogeray_b200 import synth
