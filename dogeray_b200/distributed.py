@@ -31,6 +31,16 @@ def shard_tiles(rank: int, world: int) -> Tuple[int, int]:
     return rank, world
 
 
+def tile_owner_mask(width: int, height: int, rank: int, world: int):
+    """(H, W) bool array: the pixels `rank` owns under interleaved tile sharding -- tile t = (y // 4) * ceil(W / 8) +
+    x // 8 belongs to rank t % world (slot_to_pixel / k_resolve in csrc/render.cu, drb_render_multi's merge)."""
+    import numpy as np
+    tile_rank, tile_count = shard_tiles(rank, world)
+    tiles_x = (width + 7) // 8
+    y, x = np.mgrid[0:height, 0:width]
+    return ((y // 4) * tiles_x + x // 8) % tile_count == tile_rank
+
+
 def env_rank_world() -> Tuple[int, int, int]:
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 

@@ -24,6 +24,22 @@ def test_shard_samples_partitions_exactly():
         shard_samples(4, 2, 2)
 
 
+def test_tile_owner_masks_partition_the_image():
+    from dogeray_b200.distributed import shard_tiles, tile_owner_mask
+    for (w, h) in ((64, 40), (70, 45), (7, 3), (1920, 1080)):
+        for world in (1, 2, 3, 8):
+            masks = [tile_owner_mask(w, h, r, world) for r in range(world)]
+            assert np.sum(masks, axis=0).min() == 1 and np.sum(masks, axis=0).max() == 1      # every pixel exactly once
+            if w >= 16 and world > 1:
+                assert not masks[0][0, 8] and masks[1][0, 8] and masks[0][0, :8].all()         # neighbouring tiles alternate
+            counts = [int(m.sum()) for m in masks]
+            if (w, h) == (1920, 1080):
+                assert max(counts) - min(counts) <= 32 * 2                                     # balanced to a couple of tiles
+    assert shard_tiles(1, 4) == (1, 4)
+    with pytest.raises(ValueError):
+        shard_tiles(4, 4)
+
+
 WORKER = r'''
 import os, sys
 import numpy as np
@@ -65,6 +81,16 @@ if rank == 0:
     err = float(np.abs(last.numpy() / st.spp * 255.0 - full).max())
     print("PROGRESSIVE_MAXERR %g" % err)
     assert err < 2e-3, err
+# tile sharding: each rank contributes only the pixels of its tiles; the reduced image IS the full frame, bit for bit
+from dogeray_b200.distributed import tile_owner_mask
+r.apply(st); r.set_seed(3)
+whole, _, _ = r.frame(1, 0, threads=1)                          # (W, H, 3)
+mine = tile_owner_mask(st.width, st.height, rank, world).T      # (W, H)
+part = torch.from_numpy(np.where(mine[:, :, None], whole, np.float32(0)))
+dist.reduce(part, dst=0)
+if rank == 0:
+    assert np.array_equal(part.numpy(), whole)
+    print("TILES_BIT_IDENTICAL")
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -79,4 +105,4 @@ def test_two_rank_gloo_sample_sharding(tmp_path):
            "--master-port", "29533", str(script), ROOT, str(tmp_path)]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "MAXERR" in p.stdout and "PROGRESSIVE_MAXERR" in p.stdout
+    assert "MAXERR" in p.stdout and "PROGRESSIVE_MAXERR" in p.stdout and "TILES_BIT_IDENTICAL" in p.stdout

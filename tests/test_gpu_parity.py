@@ -443,6 +443,10 @@ def test_tile_sharding_is_bit_identical_to_the_whole_image():
     nz = [(p != 0).any(axis=2) for p in parts]
     assert not (nz[0] & nz[1]).any() and not (nz[0] & nz[2]).any() and not (nz[1] & nz[2]).any()      # disjoint pixels
     assert np.array_equal(parts[0] + parts[1] + parts[2], full)                                        # bit-identical
+    from dogeray_b200.distributed import tile_owner_mask
+    for r in range(3):                                                                                  # the host-side ownership formula is the kernel's
+        m = tile_owner_mask(st.width, st.height, r, 3)
+        assert not nz[r][~m].any() and np.array_equal(parts[r][m], full[m])
     with pytest.raises(drb.DogerayError):
         sc.render(st, tile_rank=3, tile_count=3)
 
