@@ -2,12 +2,25 @@
 #pragma once
 #include "dogeray_b200.h"
 #include <cstdarg>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
+
+// std::allocator whose value-less construct() default-initialises: resize(n) on a vector of PODs then leaves the
+// memory untouched, so the parse threads are the first to touch (and fill) the pages they own
+template <class T> struct drb_default_init_alloc : std::allocator<T> {
+    template <class U> struct rebind { using other = drb_default_init_alloc<U>; };
+    drb_default_init_alloc() = default;
+    template <class U> drb_default_init_alloc(const drb_default_init_alloc<U>&) noexcept {}
+    template <class U> void construct(U* p) noexcept { ::new ((void*)p) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+using drb_object_vector = std::vector<drb_object, drb_default_init_alloc<drb_object>>;
 
 struct drb_host_scene {
     drb_settings settings;
-    std::vector<drb_object> objects;
+    drb_object_vector objects;
     std::vector<std::string> tex_paths;   // candidate texture files, sorted
     int64_t skipped = 0;                  // lines that were not turned into objects
     std::string first_warning;

@@ -111,10 +111,12 @@ void parse_object_line(const char* p, const char* e, uint64_t lineno, const std:
     int col = 0;
     const char* q = p;
     for (;;) {
-        const char* c = (const char*)memchr(q, ',', (size_t)(e - q));
+        const char* c = q;                              // tokens are ~9 characters: a byte loop beats a memchr call
+        while (c < e && *c != ',') ++c;
+        if (c == e) c = nullptr;
         Token t{ q, (size_t)((c ? c : e) - q) };
         float f = 0; int32_t iv = 0;
-        bool is_r = token_is(t, "r");
+        const bool is_r = t.n == 1 && *t.p == 'r';
         auto F = [&]() -> float {
             if (is_r) return hash_unit(lineno, (uint32_t)col);
             if (!parse_float(t, f)) throw ParseError{ "line " + std::to_string(lineno) + " column " + std::to_string(col) + ": not a number: '" + std::string(t.p, t.n) + "'" };
@@ -190,87 +192,122 @@ void parse_settings_line(const char* p, const char* e, uint64_t lineno, const st
     }
 }
 
+// Whole-file parse, every phase parallel over byte ranges that end on line boundaries:
+//   A  each thread splits its range into lines (std::getline semantics: a final line without '\n' counts, an empty
+//      tail does not) and classifies them: blank (skipped), '/' comment, '*' settings, object
+//   B  (serial, a few microseconds) prefix sums give every range its first line number and first object index;
+//      settings lines are applied in file order
+//   C  each thread parses the object lines of its own range straight into the (uninitialised) object array and
+//      checks that the tracer can represent them
+// Results do not depend on the thread count: line numbers, object indices, the first warning and the first error
+// are the ones a sequential pass would report.
 int parse_buffer(const char* text, size_t len, const char* tex_dir, drb_host_scene** out)
 {
     auto hs = new drb_host_scene();
     drb_settings_default(&hs->settings);
     hs->tex_paths = drb_scan_textures(tex_dir);
 
-    // pass 1: line table (std::getline semantics: a final line without '\n' counts, an empty tail does not)
     struct Line { const char* b; const char* e; };
-    std::vector<Line> lines;
-    lines.reserve(len / 64 + 16);
-    const char* p = text; const char* end = text + len;
-    while (p < end) {
-        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-        const char* le = nl ? nl : end;
-        lines.push_back({ p, le });
-        p = nl ? nl + 1 : end;
-    }
-    // classify; object index = count of earlier object lines
-    std::vector<int64_t> obj_line;      // line number of each object
-    obj_line.reserve(lines.size());
-    std::string err;
-    for (size_t i = 0; i < lines.size(); ++i) {
-        const char* b = lines[i].b; const char* e = lines[i].e;
-        if (e > b && e[-1] == '\r') { --e; lines[i].e = e; }       // text-mode read on the reference's platform
-        if (b == e) {
-            hs->skipped++;
-            if (hs->first_warning.empty()) hs->first_warning = "line " + std::to_string(i + 1) + ": blank line skipped";
-            continue;
-        }
-        if (*b == '/') continue;
-        if (*b == '*') {
-            try { parse_settings_line(b, e, i + 1, hs->tex_paths, hs->settings); }
-            catch (ParseError& pe) { err = pe.msg; break; }
-            continue;
-        }
-        obj_line.push_back((int64_t)i);
-    }
-    if (!err.empty()) { drb_set_error("%s", err.c_str()); delete hs; return DRB_ERR_PARSE; }
-
-    // pass 2: objects, parallel over contiguous ranges
-    const int64_t n = (int64_t)obj_line.size();
-    hs->objects.resize((size_t)n);
+    struct Range {
+        const char* b; const char* e;
+        std::vector<Line> obj;                // object lines
+        std::vector<int64_t> obj_local;       // their line index inside the range
+        std::vector<std::pair<int64_t, Line>> settings;
+        int64_t nlines = 0, blank = 0, first_blank = -1;
+        int64_t line_base = 0, obj_base = 0;
+        // phase C
+        int64_t bad = 0, first_bad_line = -1; int first_bad_type = 0, first_bad_cols = 0;
+        int64_t err_line = -1; std::string err;
+    };
     unsigned hw = std::thread::hardware_concurrency();
-    int nthreads = (int)std::min<int64_t>(hw ? hw : 4, std::max<int64_t>(1, n / 20000));
-    std::mutex err_mu;
-    int64_t err_line = INT64_MAX;
-    auto work = [&](int64_t lo, int64_t hi) {
-        for (int64_t k = lo; k < hi; ++k) {
-            const Line& L = lines[(size_t)obj_line[k]];
-            try { parse_object_line(L.b, L.e, (uint64_t)obj_line[k] + 1, hs->tex_paths, hs->objects[(size_t)k]); }
-            catch (ParseError& pe) {
-                std::lock_guard<std::mutex> g(err_mu);
-                if (obj_line[k] < err_line) { err_line = obj_line[k]; err = pe.msg; }
-                return;
+    const int nthreads = (int)std::min<size_t>(hw ? hw : 4, std::max<size_t>(1, len >> 20));
+    std::vector<Range> rg((size_t)nthreads);
+    const char* end = text + len;
+    {
+        const char* b = text;
+        for (int t = 0; t < nthreads; ++t) {
+            const char* e = end;
+            if (t + 1 < nthreads) {
+                const char* guess = text + len * (size_t)(t + 1) / (size_t)nthreads;
+                if (guess < b) guess = b;
+                const char* nl = (const char*)memchr(guess, '\n', (size_t)(end - guess));
+                e = nl ? nl + 1 : end;
+            }
+            rg[(size_t)t].b = b; rg[(size_t)t].e = e;
+            b = e;
+        }
+    }
+    auto run = [&](auto&& fn) {
+        if (nthreads <= 1) { fn(0); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(fn, t);
+        for (auto& th : pool) th.join();
+    };
+
+    // ---- A: lines ----
+    run([&](int t) {
+        Range& r = rg[(size_t)t];
+        r.obj.reserve((size_t)(r.e - r.b) / 200 + 16);
+        r.obj_local.reserve((size_t)(r.e - r.b) / 200 + 16);
+        const char* p = r.b;
+        while (p < r.e) {
+            const char* nl = (const char*)memchr(p, '\n', (size_t)(r.e - p));
+            const char* b = p; const char* e = nl ? nl : r.e;
+            p = nl ? nl + 1 : r.e;
+            const int64_t idx = r.nlines++;
+            if (e > b && e[-1] == '\r') --e;                           // text-mode read on the reference's platform
+            if (b == e) { r.blank++; if (r.first_blank < 0) r.first_blank = idx; continue; }
+            if (*b == '/') continue;
+            if (*b == '*') { r.settings.push_back({ idx, Line{ b, e } }); continue; }
+            r.obj.push_back(Line{ b, e });
+            r.obj_local.push_back(idx);
+        }
+    });
+
+    // ---- B: numbering, settings ----
+    int64_t nlines = 0, n = 0;
+    for (Range& r : rg) { r.line_base = nlines; r.obj_base = n; nlines += r.nlines; n += (int64_t)r.obj.size(); }
+    for (Range& r : rg) {
+        if (r.blank) {
+            hs->skipped += r.blank;
+            if (hs->first_warning.empty()) hs->first_warning = "line " + std::to_string(r.line_base + r.first_blank + 1) + ": blank line skipped";
+        }
+    }
+    for (Range& r : rg)
+        for (auto& sl : r.settings) {
+            try { parse_settings_line(sl.second.b, sl.second.e, (uint64_t)(r.line_base + sl.first + 1), hs->tex_paths, hs->settings); }
+            catch (ParseError& pe) { drb_set_error("%s", pe.msg.c_str()); delete hs; return DRB_ERR_PARSE; }
+        }
+
+    // ---- C: objects ----
+    hs->objects.resize((size_t)n);                                     // default-initialised: first touched by its parser
+    run([&](int t) {
+        Range& r = rg[(size_t)t];
+        for (size_t k = 0; k < r.obj.size(); ++k) {
+            const int64_t line = r.line_base + r.obj_local[k];         // zero-based
+            drb_object& o = hs->objects[(size_t)r.obj_base + k];
+            try { parse_object_line(r.obj[k].b, r.obj[k].e, (uint64_t)line + 1, hs->tex_paths, o); }
+            catch (ParseError& pe) { r.err_line = line; r.err = pe.msg; return; }
+            // objects the tracer cannot represent are kept (ids are line indices) but reported
+            const bool ok = (o.type == 2 && o.ncols >= 16) || (o.type == 0 && o.ncols >= 10);
+            if (!ok) {
+                if (!r.bad++) { r.first_bad_line = line; r.first_bad_type = o.type; r.first_bad_cols = o.ncols; }
             }
         }
-    };
-    if (nthreads <= 1) work(0, n);
-    else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nthreads; ++t) pool.emplace_back(work, n * t / nthreads, n * (t + 1) / nthreads);
-        for (auto& th : pool) th.join();
-    }
-    if (!err.empty()) { drb_set_error("%s", err.c_str()); delete hs; return DRB_ERR_PARSE; }
-
-    // objects the tracer cannot represent are kept (ids are line indices) but reported
-    for (int64_t k = 0; k < n; ++k) {
-        const drb_object& o = hs->objects[(size_t)k];
-        bool ok = (o.type == 2 && o.ncols >= 16) || (o.type == 0 && o.ncols >= 10);
-        if (!ok) {
-            hs->skipped++;
-            if (hs->first_warning.empty())
-                hs->first_warning = "line " + std::to_string(obj_line[k] + 1) + ": object with type " + std::to_string(o.type) + " and " +
-                                    std::to_string(o.ncols) + " columns is not renderable (types: 0 sphere, 2 triangle) and is left out of the tree";
-        }
+    });
+    for (Range& r : rg)                                                // ranges are in file order: the first error wins
+        if (r.err_line >= 0) { drb_set_error("%s", r.err.c_str()); delete hs; return DRB_ERR_PARSE; }
+    for (Range& r : rg) {
+        if (!r.bad) continue;
+        hs->skipped += r.bad;
+        if (hs->first_warning.empty())
+            hs->first_warning = "line " + std::to_string(r.first_bad_line + 1) + ": object with type " + std::to_string(r.first_bad_type) + " and " +
+                                std::to_string(r.first_bad_cols) + " columns is not renderable (types: 0 sphere, 2 triangle) and is left out of the tree";
     }
     if (!hs->first_warning.empty()) drb_set_error("%s", hs->first_warning.c_str());
     *out = hs;
     return DRB_OK;
 }
-
 
 // ---- binary scene cache ("optional binary cache keyed by file hash") -------------------
 // 64-bit content hash: 1 MiB chunks hashed independently (multiply-fold over 8-byte words, threads over

@@ -121,6 +121,64 @@ def test_large_parse_is_parallel_and_ordered(tmp_path):
     assert r.num_objects == len(objs)
 
 
+def _numbered_scene(nlines, seed):
+    """text whose object line k carries k in its first column, with comments, blank lines, CRLF endings, ragged line
+    lengths and one settings line sprinkled in; returns (text, expected first-column values, blank count, first blank line)"""
+    rng = np.random.default_rng(seed)
+    out, expect, blanks, first_blank = [], [], 0, None
+    kinds = rng.integers(0, 100, nlines)
+    for i in range(nlines):
+        k = kinds[i]
+        if k < 3:
+            out.append(b"/ comment %d" % i + b" x" * int(rng.integers(0, 40)))
+        elif k < 5:
+            out.append(b"")
+            blanks += 1
+            first_blank = i + 1 if first_blank is None else first_blank
+        elif i == nlines // 2:
+            out.append(b"*,1,2,3,0.01,0,0,0,3,45,7,9,1,no,64,32")
+        else:
+            v = len(expect)
+            cols = [b"%d" % v, b"1", b"2", b"2", b"0.5", b"0.5", b"0.5", b"0", b"0", b"1", b"0", b"0", b"0", b"0", b"1", b"0"]
+            cols += [b"0.25"] * int(rng.integers(0, 20))                # ragged: 16..35 columns
+            out.append(b",".join(cols) + (b"\r" if k % 2 else b""))
+            expect.append(v)
+    return b"\n".join(out), np.array(expect, np.float32), blanks, first_blank
+
+
+def test_parallel_parse_numbers_lines_like_a_sequential_pass(tmp_path):
+    """> 8 MiB of text: every byte range, chunk boundary and prefix sum of the parallel parser is exercised; object
+    order, skipped count, the first warning and the line number of an injected error must be the sequential ones"""
+    text, expect, blanks, first_blank = _numbered_scene(150_000, seed=2)
+    assert len(text) > 8 << 20
+    for tail in (b"", b"\n"):                                            # with and without a final newline
+        hs = drb.HostScene.parse(text + tail)
+        o = hs.objects()
+        assert len(o) == len(expect) and np.array_equal(o["pos"][:, 0], expect)
+        assert hs.num_skipped == blanks and ("line %d: blank line skipped" % first_blank).encode() in drb._lib.drb_last_error()
+        assert hs.settings.max_depth == 7 and hs.settings.spp == 9 and (hs.settings.width, hs.settings.height) == (64, 32)
+    p = str(tmp_path / "n.rts")
+    open(p, "wb").write(text)
+    assert np.array_equal(drb.HostScene.load(p).objects().view(np.uint8), o.view(np.uint8))
+    # an error far into the file is reported with its own line number; of two errors the earlier one wins
+    lines = text.split(b"\n")
+    bad = [i for i, l in enumerate(lines) if l[:1] not in (b"", b"/", b"*")]
+    first, second = bad[len(bad) // 3], bad[2 * len(bad) // 3]
+    for i in (second, first):
+        lines[i] = lines[i].replace(b",2,0.5,", b",2,oops,", 1)
+        with pytest.raises(drb.DogerayError) as e:
+            drb.HostScene.parse(b"\n".join(lines))
+        assert e.value.status == drb.ERR_PARSE and "line %d column 4" % (i + 1) in str(e.value)
+    # an unrenderable object is a warning only when no blank line came first
+    clean = b"\n".join(l for l in text.split(b"\n") if l != b"")
+    cl = clean.split(b"\n")
+    idx = [i for i, l in enumerate(cl) if l[:1] not in (b"/", b"*")][1000]
+    cl[idx] = cl[idx].replace(b",1,2,2,", b",1,2,7,", 1)                  # type 7: kept, not renderable
+    hs = drb.HostScene.parse(b"\n".join(cl))
+    assert hs.num_skipped == 1 and ("line %d: object with type 7" % (idx + 1)).encode() in drb._lib.drb_last_error()
+    assert hs.num_objects == len(expect)
+
+
 def test_rts_writer_is_exporter_format(tmp_path):
     objs, st = synth.heightfield_scene(n=2)
     p = str(tmp_path / "w.rts")
