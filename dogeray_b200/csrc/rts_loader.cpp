@@ -397,7 +397,18 @@ drb_host_scene* cache_read(const std::string& path, uint64_t source_hash, uint64
                 const char* q = (const char*)m + sizeof h;
                 hs->first_warning.assign(q, h.warning_len);
                 const drb_object* o = (const drb_object*)(q + wl);
-                hs->objects.assign(o, o + h.nobjects);
+                // copy in parallel: page faults on both sides are most of the cost of a 100+ MB copy
+                const size_t nobj = (size_t)h.nobjects;
+                hs->objects.resize(nobj);                              // default-initialised, see drb_default_init_alloc
+                unsigned hw = std::thread::hardware_concurrency();
+                const size_t nt = std::min<size_t>(hw ? hw : 4, std::max<size_t>(1, nobj / 65536));
+                auto copy = [&](size_t lo, size_t hi) { if (hi > lo) memcpy(hs->objects.data() + lo, o + lo, (hi - lo) * sizeof(drb_object)); };
+                if (nt <= 1) copy(0, nobj);
+                else {
+                    std::vector<std::thread> pool;
+                    for (size_t t = 0; t < nt; ++t) pool.emplace_back(copy, nobj * t / nt, nobj * (t + 1) / nt);
+                    for (auto& th : pool) th.join();
+                }
             }
             munmap(m, len);
         }
