@@ -85,6 +85,16 @@ def measured_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_counters():
+    """ncu counters of k_trace from this round's committed capture (profiles/trace_counters.json): what actually limits it"""
+    p = os.path.join(ROOT, "profiles", "trace_counters.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def profiled_traffic():
     """dram bytes per k_trace launch from the committed ncu capture, if one was recorded"""
     p = os.path.join(ROOT, "profiles", "trace_traffic.json")
@@ -163,6 +173,7 @@ class StdoutToStderr:
 
 
 _SCENE_FILE = {}
+LAST_CPU_FRAME = {}      # the CPU baseline's last frame (255 * mean, (W, H, 3)) with its sample range: the bench line's parity check
 
 
 def scene_file(objs, st):
@@ -210,46 +221,82 @@ def cpu_reference_arm(objs, st, desc, spp_sample, steps, warmup, threads):
         frame(1000 + w)
     rays = 0; t1 = time.time()
     for k in range(steps):
-        _, _, r = frame(k * spp_sample)
+        f, _, r = frame(k * spp_sample)
         rays += r
     dt = time.time() - t1
     paths = st.width * st.height * spp_sample * steps
+    LAST_CPU_FRAME["frame"], LAST_CPU_FRAME["base"], LAST_CPU_FRAME["spp"], LAST_CPU_FRAME["rays"] = f, (steps - 1) * spp_sample, spp_sample, r
     return rays / dt / 1e6, dt / steps * 1e3, kind, rays / max(paths, 1)
 
 
-def ref_gpu_baseline(objs, st, spp_sample, rays_per_path):
-    """kernel.cu rebuilt for sm_100: kernel-only (CUDA events, resident buffers) and one CudaStarter call."""
+def ref_gpu_baseline(objs, st, spp_sample):
+    """kernel.cu rebuilt for sm_100, kernel-only (CUDA events, resident buffers) at `spp_sample` spp of the same frame.
+    Rays are the reference's OWN count: the same launch of the instrumented build (a counter in front of raycolor's
+    hit() call, oracle/make_ref.py build_gpu_counting), which is never the build that is timed."""
     import ctypes as C
     import numpy as np
-    import dogeray_b200 as drb
     lib = os.path.join(ROOT, "oracle", "_ref", "libdogeray_ref_gpu.so")
+    lib_count = os.path.join(ROOT, "oracle", "_ref", "libdogeray_ref_gpu_count.so")
     if not os.path.exists(lib):
         return {"unavailable": "oracle/_ref/libdogeray_ref_gpu.so not built"}
-    L = C.CDLL(lib)
-    L.refgpu_load.argtypes = [C.c_char_p, C.c_char_p]
-    L.refgpu_set_settings.argtypes = [C.c_void_p]
-    L.refgpu_kernel_only.argtypes = [C.c_void_p, C.c_int, C.c_int]; L.refgpu_kernel_only.restype = C.c_float
-    L.refgpu_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     path, tmp = scene_file(objs, st)
-    t0 = time.time()
-    n = L.refgpu_load(os.fsencode(path), os.fsencode(tmp))
-    if n <= 0:
-        return {"unavailable": "refgpu_load returned %d" % n}
-    load_s = time.time() - t0
     sv = np.array([st.cam[0], st.cam[1], st.cam[2], st.aperture, st.look[0], st.look[1], st.look[2], st.focus, st.fov, st.max_depth,
                    spp_sample, st.bg_intensity, st.backtex, st.width, st.height, 0], np.float32)
-    L.refgpu_set_settings(sv.ctypes.data)
     out = np.zeros((st.width, st.height, 3), np.int32)
-    L.refgpu_kernel_only(out.ctypes.data, 1, 1)                       # warm-up
-    ms = L.refgpu_kernel_only(out.ctypes.data, 1, 2)
-    wall = C.c_double(0)
-    L.refgpu_frame(out.ctypes.data, 1, C.byref(wall))
     paths = st.width * st.height * spp_sample
-    rays = paths * rays_per_path
-    return {"kernel_only_mrays_s": rays / (ms * 1e-3) / 1e6 if ms > 0 else None, "kernel_ms": ms,
-            "cudastarter_call_mrays_s": rays / (wall.value * 1e-3) / 1e6 if wall.value > 0 else None, "cudastarter_ms": wall.value,
-            "sample": "same frame at %d spp (kernel.cu unmodified, nvcc -arch=sm_100); rays = paths x %.4f rays/path measured by our kernel on this scene" % (spp_sample, rays_per_path),
+
+    def load(libpath):
+        L = C.CDLL(libpath)
+        L.refgpu_load.argtypes = [C.c_char_p, C.c_char_p]
+        L.refgpu_set_settings.argtypes = [C.c_void_p]
+        L.refgpu_kernel_only.argtypes = [C.c_void_p, C.c_int, C.c_int]; L.refgpu_kernel_only.restype = C.c_float
+        L.refgpu_rays.argtypes = [C.c_int]; L.refgpu_rays.restype = C.c_longlong
+        t0 = time.time()
+        n = L.refgpu_load(os.fsencode(path), os.fsencode(tmp))
+        if n <= 0:
+            raise RuntimeError("refgpu_load returned %d" % n)
+        L.refgpu_set_settings(sv.ctypes.data)
+        return L, time.time() - t0
+
+    rays, rays_src = None, None
+    if os.path.exists(lib_count):
+        Lc, _ = load(lib_count)
+        Lc.refgpu_rays(1)
+        if Lc.refgpu_kernel_only(out.ctypes.data, 1, 1) > 0:
+            rays = int(Lc.refgpu_rays(1))
+            rays_src = "counted by the reference's own raycolor (instrumented build, separate untimed launch at the same spp)"
+        Lc.refgpu_free()
+    L, load_s = load(lib)
+    L.refgpu_kernel_only(out.ctypes.data, 1, 1)                       # warm-up
+    launches = 3
+    ms = L.refgpu_kernel_only(out.ctypes.data, 1, launches)
+    L.refgpu_free()
+    if rays is None:
+        return {"unavailable": "the ray-counting build of the reference is missing: no ray count of its own"}
+    return {"kernel_only_mrays_s": rays / (ms * 1e-3) / 1e6 if ms > 0 else None, "kernel_ms": ms, "launches_timed": launches,
+            "spp": spp_sample, "paths": paths, "rays": rays, "rays_per_path": rays / paths, "rays_source": rays_src,
+            "sample": "same frame at %d of %d spp (kernel.cu unmodified, nvcc -arch=sm_100, kernel only from resident buffers, mean of %d launches after one warm-up)"
+                      % (spp_sample, st.spp, launches),
             "host_parse_build_s": round(load_s, 2), "mean_pixel": float(out.mean())}
+
+
+def parity_against_cpu_frame(drb, device, kind):
+    """The CPU baseline leg rendered `spp` samples of the frame from the .rts text with the reference's own code; render
+    the same sample range of the same text on the GPU and compare: the bench line carries its own parity evidence."""
+    import numpy as np
+    if "frame" not in LAST_CPU_FRAME or "path" not in _SCENE_FILE:
+        return None
+    f, base, spp, cpu_rays = LAST_CPU_FRAME["frame"], LAST_CPU_FRAME["base"], LAST_CPU_FRAME["spp"], LAST_CPU_FRAME["rays"]
+    hs = drb.HostScene.load(_SCENE_FILE["path"], _SCENE_FILE["dir"])
+    sc = drb.Scene.from_host(hs, device=device)
+    st = sc.settings
+    acc, stats = sc.render(st, seed=0, sample_base=base, sample_count=spp)
+    sc.close(); hs.close()
+    ours = acc.transpose(1, 0, 2) * np.float32(255.0) * np.float32(1.0 / spp)
+    diff = (ours.astype(np.float64) - f.astype(np.float64)) / 255.0
+    return {"against": "cpu_baseline frame (%s), samples [%d, %d) of every pixel, %d x %d" % (kind, base, base + spp, st.width, st.height),
+            "identical": float(np.mean(np.all(ours == f, axis=-1))), "rmse": float(np.sqrt(np.mean(diff ** 2))),
+            "max_abs": float(np.abs(diff).max()), "rays_equal": bool(stats.rays == cpu_rays), "rays": int(stats.rays), "cpu_rays": int(cpu_rays)}
 
 
 def emit(line):
@@ -379,15 +426,35 @@ def main():
     image_mean = float(accum.mean().item()) / max(st.spp, 1) if rank == 0 else 0.0
 
     # ---- e2e: host buffers in, host image out, every step -------------------------------------------------
+    # One CudaStarter call of the reference uploads the whole scene, renders and downloads (kernel.cu:2604-2651).  Here,
+    # per step: the object lines go host -> device from pinned memory (N > 1: rank r uploads lines [r*chunk, (r+1)*chunk)
+    # and ONE all-gather over NVLink completes the array on every GPU, so the node pays the PCIe upload once, not N
+    # times), the tree is rebuilt on the GPU, the frame is rendered, reduced, and the float image is read back.
     host_img = torch.empty(st.height, st.width, 3, pin_memory=True)
-    h2d = hs.num_objects * drb.OBJECT_DTYPE.itemsize
+    nobj = hs.num_objects
+    rec = drb.OBJECT_DTYPE.itemsize
     d2h = st.height * st.width * 3 * 4
+    if world > 1:
+        chunk = (nobj + world - 1) // world
+        lo, hi = min(nobj, rank * chunk), min(nobj, (rank + 1) * chunk)
+        mine = torch.zeros(chunk * rec, dtype=torch.uint8).pin_memory()
+        mine[: (hi - lo) * rec] = torch.from_numpy(hs.objects()[lo:hi].view(np.uint8).copy())
+        gathered = torch.empty(world * chunk * rec, dtype=torch.uint8, device=dev)
+        h2d = world * chunk * rec                                  # whole job, per step
+        config["e2e_upload"] = "each rank uploads 1/%d of the object lines (%d B), one NCCL all-gather completes the array on every GPU" % (world, chunk * rec)
+    else:
+        h2d = nobj * rec
 
     e2e_parts = {"create_ms": 0.0, "render_ms": 0.0, "reduce_readback_ms": 0.0, "free_ms": 0.0}
 
     def step_e2e():
         t0 = time.perf_counter()
-        sc = drb.Scene.from_host(hs, device=local)            # H2D of every object line + GPU LBVH build
+        if world > 1:
+            part = mine.to(dev, non_blocking=True)                # H2D of this rank's share
+            dist.all_gather_into_tensor(gathered, part)
+            sc = drb.Scene.from_device_objects(hs, gathered.data_ptr(), device=local, stream=stream)   # GPU LBVH build
+        else:
+            sc = drb.Scene.from_host(hs, device=local)            # H2D of every object line + GPU LBVH build
         t1 = time.perf_counter()
         if tile_kw:
             accum.zero_()
@@ -403,7 +470,8 @@ def main():
         t4 = time.perf_counter()
         for k, v in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             e2e_parts[k] += v * 1e3
-        log("[rank %d] e2e step: create %.1f ms, render %.1f ms (device %.1f, k_trace %.1f)" % (rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, s.total_ms, s.trace_ms))
+        log("[rank %d] e2e step: create %.1f ms, render %.1f ms (device %.1f, k_trace %.1f), reduce+readback %.1f ms, free %.1f ms" %
+            (rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, s.total_ms, s.trace_ms, (t3 - t2) * 1e3, (t4 - t3) * 1e3))
         return s
 
     scene.close()
@@ -426,6 +494,9 @@ def main():
         e_rays_all, e_ms_max = float(e_rays), e_ms
     e2e_value = e_rays_all / (e_ms_max * 1e-3) / 1e6
 
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    hbm_used_gb = (total_b - free_b) / 1e9                         # scene + ray queues + cached blocks, after the last step
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         bpr = bytes_per_ray(ntris)
@@ -446,8 +517,13 @@ def main():
                          "trace_share_of_step": trace_ms / ms if ms > 0 else None,
                          "note": "algorithmic bytes = 32*ceil(log2 Ntris) + 36 + 64 per ray (SURVEY.md 8d); scenes of this size are largely L2-resident, see profiles/"},
             "clocks": clk, "image_mean_radiance": image_mean,
-            "build": {"upload_ms": bi.upload_ms, "lbvh_build_ms": bi.build_ms, "tree_height": bi.max_depth},
+            "build": {"upload_ms": bi.upload_ms, "lbvh_build_ms": bi.build_ms, "tree_height": bi.max_depth, "wide_nodes": int(bi.nwide),
+                      "wide_levels": bi.wide_levels, "stack_levels": bi.stack_levels},
+            "hbm_in_use_gb": hbm_used_gb,
         }
+        counters = profiled_counters()
+        if counters:
+            line["roofline"].update(counters)
         if world == 1 and not args.no_baselines:
             rpp = rays_all / max(paths_all, 1.0)
             try:
@@ -456,11 +532,12 @@ def main():
                     v, cms, kind, _ = cpu_reference_arm(objs, st, desc, spp_s, 1, 0, ncores)
                 line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": ncores, "kind": kind,
                                         "sample": "%d of %d spp of the same frame on %d host threads, %.1f s" % (spp_s, st.spp, ncores, cms / 1e3)}
+                line["parity"] = parity_against_cpu_frame(drb, local, kind)
             except Exception as ex:                                  # the baseline must never cost the measurement
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": ncores, "kind": "port", "sample": "failed: %r" % (ex,)}
             try:
                 with StdoutToStderr():
-                    line["ref_gpu"] = ref_gpu_baseline(objs, st, 4, rpp)
+                    line["ref_gpu"] = ref_gpu_baseline(objs, st, 32)
             except Exception as ex:
                 line["ref_gpu"] = {"unavailable": repr(ex)}
             scene_file_cleanup()

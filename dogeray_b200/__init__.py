@@ -29,7 +29,9 @@ _lib = C.CDLL(LIB_PATH)
 
 OK, ERR_ARG, ERR_IO, ERR_PARSE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 FLAG_ACCUMULATE = 1
+FLAG_EXACT_SAMPLES = 2
 BUILD_LBVH_ONLY = 1
+BUILD_KEEP_DEBUG = 2
 
 
 class DogerayError(RuntimeError):
@@ -100,7 +102,7 @@ class BuildInfo(C.Structure):
     _fields_ = [
         ("nprims", C.c_int64), ("nnodes", C.c_int64), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3),
         ("upload_ms", C.c_float), ("build_ms", C.c_float), ("max_depth", C.c_int32), ("rebuild_iterations", C.c_int32),
-        ("nwide", C.c_int64), ("wide_levels", C.c_int32),
+        ("nwide", C.c_int64), ("wide_levels", C.c_int32), ("stack_levels", C.c_int32),
     ]
 
 
@@ -127,10 +129,12 @@ _sig("drb_host_scene_settings", _i, _vp, C.POINTER(Settings))
 _sig("drb_host_scene_num_textures", _i, _vp)
 _sig("drb_host_scene_texture_path", _cp, _vp, _i)
 _sig("drb_host_scene_num_skipped", _i64, _vp)
+_sig("drb_host_scene_num_renderable", _i64, _vp)
 _sig("drb_rts_write", _i, _cp, C.POINTER(Settings), _vp, _i64, C.POINTER(_cp), _i, _cp)
 _sig("drb_settings_default", None, C.POINTER(Settings))
 _sig("drb_scene_create", _i, _vp, _i, _pp)
 _sig("drb_scene_create_ex", _i, _vp, _i, _u32, _pp)
+_sig("drb_scene_create_from_device", _i, _vp, _i, _u32, _vp, _vp, _pp)
 _sig("drb_scene_tree", _i, _vp, _vp, _vp, _vp, _vp)
 _sig("drb_scene_wide", _i, _vp, _vp, _vp)
 _sig("drb_scene_load", _i, _cp, _cp, _i, _pp)
@@ -163,7 +167,8 @@ EXPORTED_SYMBOLS = [
     "drb_host_scene_load", "drb_host_scene_load_cached", "drb_hash_bytes", "drb_host_scene_parse", "drb_host_scene_create",
     "drb_host_scene_free",
     "drb_host_scene_num_objects", "drb_host_scene_objects", "drb_host_scene_settings",
-    "drb_host_scene_num_textures", "drb_host_scene_texture_path", "drb_host_scene_num_skipped",
+    "drb_host_scene_num_textures", "drb_host_scene_texture_path", "drb_host_scene_num_skipped", "drb_host_scene_num_renderable",
+    "drb_scene_create_from_device",
     "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_create_ex", "drb_scene_tree", "drb_scene_wide", "drb_scene_load", "drb_scene_free",
     "drb_scene_settings", "drb_scene_num_prims", "drb_scene_num_objects", "drb_scene_build_info",
     "drb_scene_lbvh", "drb_opts_default", "drb_render_device", "drb_render", "drb_render_multi", "drb_frame_i3",
@@ -196,7 +201,7 @@ def device_count() -> int:
     return int(_lib.drb_device_count())
 
 
-def render_multi(scenes: Sequence["Scene"], settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=0,
+def render_multi(scenes: Sequence["Scene"], settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=None,
                  batch_paths=0, accumulate_into: Optional[np.ndarray] = None) -> Tuple[np.ndarray, Stats]:
     """One frame over several resident scenes (the same scene on different devices) from this process: interleaved
     tile sharding, one host thread per handle, merged on the host; bit-identical to Scene.render on one handle."""
@@ -287,6 +292,10 @@ class HostScene:
         return int(_lib.drb_host_scene_num_objects(self._h))
 
     @property
+    def num_renderable(self) -> int:
+        return int(_lib.drb_host_scene_num_renderable(self._h))
+
+    @property
     def num_skipped(self) -> int:
         return int(_lib.drb_host_scene_num_skipped(self._h))
 
@@ -350,6 +359,14 @@ class Scene:
         _check(_lib.drb_scene_create_ex(hs.handle, device, build_flags, C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def from_device_objects(cls, hs: HostScene, objects_ptr: int, device: int = 0, build_flags: int = 0, stream: Optional[int] = None) -> "Scene":
+        """The object lines are already in device memory (hs.num_objects records of OBJECT_DTYPE at `objects_ptr`, e.g.
+        all-gathered over NVLink from per-rank partial uploads); `stream` is the stream that produced them."""
+        h = C.c_void_p()
+        _check(_lib.drb_scene_create_from_device(hs.handle, device, build_flags, objects_ptr, stream, C.byref(h)))
+        return cls(h)
+
     def close(self):
         if self._h and _lib is not None:             # _lib is None while the interpreter shuts down
             _lib.drb_scene_free(self._h)
@@ -408,15 +425,19 @@ class Scene:
         return dict(child=child, boxes=boxes)
 
     @staticmethod
-    def _opts(seed=0, sample_base=0, sample_count=0, batch_paths=0, flags=0, stream=None, tile_rank=0, tile_count=0) -> Opts:
+    def _opts(seed=0, sample_base=0, sample_count=None, batch_paths=0, flags=0, stream=None, tile_rank=0, tile_count=0) -> Opts:
+        """sample_count None -> the settings' spp; an integer is taken literally (0 traces nothing: the empty share of
+        a sharded frame, distributed.shard_samples with spp < ranks)"""
         o = Opts()
         _lib.drb_opts_default(C.byref(o))
-        o.seed, o.sample_base, o.sample_count, o.batch_paths, o.flags = seed, sample_base, sample_count, batch_paths, flags
+        if sample_count is not None:
+            flags |= FLAG_EXACT_SAMPLES
+        o.seed, o.sample_base, o.sample_count, o.batch_paths, o.flags = seed, sample_base, int(sample_count or 0), batch_paths, flags
         o.stream = stream
         o.tile_rank, o.tile_count = tile_rank, tile_count
         return o
 
-    def render(self, settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=0, batch_paths=0,
+    def render(self, settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=None, batch_paths=0,
                accumulate_into: Optional[np.ndarray] = None, want_stats=True, tile_rank=0, tile_count=0) -> Tuple[np.ndarray, Optional[Stats]]:
         """Sum of radiance per pixel, float32 (H, W, 3), host buffers (device->host copy included)."""
         st = settings if settings is not None else self.settings
@@ -432,7 +453,7 @@ class Scene:
         _check(_lib.drb_render(self._h, C.byref(st), C.byref(o), out.ctypes.data, C.byref(stats) if stats is not None else None))
         return out, stats
 
-    def render_device(self, accum_ptr: int, settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=0,
+    def render_device(self, accum_ptr: int, settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=None,
                       batch_paths=0, accumulate=False, stream: Optional[int] = None, want_stats=False, tile_rank=0, tile_count=0) -> Optional[Stats]:
         """Same into a DEVICE buffer of H*W*3 float32 (e.g. torch tensor .data_ptr()); asynchronous unless want_stats."""
         st = settings if settings is not None else self.settings
@@ -441,7 +462,7 @@ class Scene:
         _check(_lib.drb_render_device(self._h, C.byref(st), C.byref(o), accum_ptr, C.byref(stats) if stats is not None else None))
         return stats
 
-    def frame_i3(self, settings: Optional[Settings] = None, divisor: int = 1, *, seed=0, sample_base=0, sample_count=0,
+    def frame_i3(self, settings: Optional[Settings] = None, divisor: int = 1, *, seed=0, sample_base=0, sample_count=None,
                  out: Optional[np.ndarray] = None) -> np.ndarray:
         """One CudaStarter call: int32 (W, H, 3) indexed [x, y] = outputr[x*H + y] (kernel.cu:1006, 1083-1085)."""
         st = settings if settings is not None else self.settings

@@ -82,7 +82,7 @@ struct DevTexture {
     int32_t w, h;
 };
 
-struct LbvhDebug {              // integer outputs of the build, kept for drb_scene_lbvh
+struct LbvhDebug {              // integer outputs of the build, kept for drb_scene_lbvh (DRB_BUILD_KEEP_DEBUG only)
     uint64_t* keys = nullptr;   // n, sorted
     int32_t* order = nullptr;   // n
     int32_t* parent = nullptr;  // n-1
@@ -92,7 +92,7 @@ struct LbvhDebug {              // integer outputs of the build, kept for drb_sc
     float4* node_max = nullptr; // n-1
 };
 
-struct FinalTree {              // the hierarchy the nodes were emitted from (root = node 0), for drb_scene_tree
+struct FinalTree {              // the hierarchy the nodes were emitted from (root = node 0), for drb_scene_tree (DRB_BUILD_KEEP_DEBUG only)
     int32_t* left = nullptr;    // n-1
     int32_t* right = nullptr;   // n-1
     float4* node_min = nullptr; // n-1
@@ -110,6 +110,7 @@ struct drb_scene {
     WideNode* wnodes = nullptr; // the traversal structure
     int64_t nwnodes = 0;
     int wide_levels = 0;        // height of the wide tree (levels of the breadth-first collapse)
+    int stack_levels = 3;       // traversal stack entries a lane can need (exact bound from the collapse + sentinel + 1)
     Prim* prims = nullptr;
     ShadeRec* recs = nullptr;
     int32_t* orig_id = nullptr; // prim slot -> object line index

@@ -25,7 +25,22 @@ struct drb_host_scene {
     int64_t skipped = 0;                  // lines that were not turned into objects
     std::string first_warning;
     mutable bool pinned = false;          // objects[] page-locked by the first drb_scene_create (scene.cu)
+    mutable int64_t renderable = -1;      // objects that go into the tree, counted on first use (drb_host_scene_num_renderable)
 };
+
+// the rule for "this object line becomes a primitive": SURVEY.md App. B.9 (types other than 0 / 2 are undefined
+// behaviour in the reference) and junk lines that stop before the geometry columns; ncols == 0 = made in memory
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline bool drb_object_renderable(const drb_object& o)
+{
+    if (o.type == 2) return o.ncols == 0 || o.ncols >= 16;
+    if (o.type == 0) return o.ncols == 0 || o.ncols >= 10;
+    return false;
+}
+// drb_host_scene_num_renderable (public) counts them once, in parallel, and remembers: the device build sizes its
+// arrays from it without reading a count back from the GPU
 // releases the page lock, if any (defined in scene.cu, the only TU that talks to CUDA about it)
 void drb_host_scene_unpin(drb_host_scene* hs);
 

@@ -346,6 +346,10 @@ __global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(D
         }
         // a lane that arrives at a leaf stashes it and keeps descending
         if (node < 0 && node != kSentinel && leaf == 0) { leaf = node; node = DRB_POP(); }
+        // an empty child slot carries the same bits as the stack-bottom sentinel; its inverted box cannot pass the slab
+        // test unless the ray's padding exceeds the whole scene (origin ~10^5 scene sizes away) -- then the stack is not
+        // empty and the link is simply dropped
+        while (node == kSentinel && sp != s_stack + threadIdx.x) node = DRB_POP();
         }
         // ---- postponed leaves -------------------------------------------------------------------------
         // The (long, divergent) primitive test runs for the whole warp at once when enough lanes hold a stashed
@@ -831,8 +835,8 @@ int ensure_buffers(drb_scene* s, size_t slots)
     DRB_CUDA(cudaMemsetAsync(q.counters, 0, CNT_WORDS * sizeof(uint32_t), st));
     DRB_CUDA(cudaStreamSynchronize(st));             // the buffers may be used from a caller-provided stream next
     rb->capacity = slots;
-    // worst case three pushes per level of the four-wide tree, plus the sentinel
-    rb->trace_smem = (size_t)(3 * std::max(s->wide_levels, 1) + 2) * kTraceThreads * sizeof(int);
+    // the exact bound the collapse computed (pushes along the worst root-to-leaf chain + sentinel + 1), not 3 per level
+    rb->trace_smem = (size_t)std::max(s->stack_levels, 3) * kTraceThreads * sizeof(int);
     return launch_shape(s->device, rb->trace_smem, &rb->trace_blocks, &rb->shade_blocks);
 }
 
@@ -858,6 +862,13 @@ int check_settings(const drb_settings* st)
     if (st->width <= 0 || st->height <= 0 || st->width > 32768 || st->height > 32768) { drb_set_error("bad image size %dx%d", st->width, st->height); return DRB_ERR_ARG; }
     if (st->max_depth < 0) { drb_set_error("bad max_depth %d", st->max_depth); return DRB_ERR_ARG; }
     return DRB_OK;
+}
+
+// samples per pixel a call traces: opts->sample_count, where 0 means "the settings' spp" unless the caller says it is exact
+uint32_t requested_samples(const drb_opts& o, const drb_settings& st)
+{
+    if (o.sample_count || (o.flags & DRB_FLAG_EXACT_SAMPLES)) return o.sample_count;
+    return (uint32_t)std::max(st.spp, 0);
 }
 
 // lanes-still-traversing threshold below which a warp refills its idle lanes (tunable for experiments)
@@ -892,7 +903,7 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
 {
     const auto t_enter = std::chrono::steady_clock::now();
     drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
-    const uint32_t total_samples = o.sample_count ? o.sample_count : (uint32_t)std::max(st->spp, 0);
+    const uint32_t total_samples = requested_samples(o, *st);
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
     DRB_CUDA(cudaSetDevice(s->device));
     if (st->backtex >= s->ntextures) { drb_set_error("settings.backtex %d out of range (scene has %d textures)", st->backtex, s->ntextures); return DRB_ERR_ARG; }
@@ -946,7 +957,13 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
     }
     uint32_t launches = 0, trace_launches = 0;
     const bool accumulate_first = (o.flags & DRB_FLAG_ACCUMULATE) != 0;
-    if (total_samples == 0 && !accumulate_first) DRB_CUDA(cudaMemsetAsync(accum, 0, (size_t)W * H * 3 * sizeof(float), stream));
+    if (total_samples == 0 && !accumulate_first) {
+        // an empty share: this call's pixels (its tiles) become 0, everything else stays as it is
+        fp.samples = 0; fp.sample_base = o.sample_base;
+        dim3 rb_block(32, 8), rb_grid((W + 31) / 32, (H + 7) / 8);
+        k_resolve<<<rb_grid, rb_block, 0, stream>>>(fp, q.contrib, accum, 0);
+        launches += 1;
+    }
 
     for (uint32_t done = 0; done < total_samples; done += per_batch) {
         fp.samples = std::min(per_batch, total_samples - done);
@@ -1137,7 +1154,7 @@ int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opt
     drb_opts o; if (opts) o = *opts; else drb_opts_default(&o);
     o.flags &= ~DRB_FLAG_ACCUMULATE;
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : s->stream;
-    const uint32_t spp = o.sample_count ? o.sample_count : (uint32_t)std::max(settings->spp, 0);
+    const uint32_t spp = requested_samples(o, *settings);
     const size_t nfull = (size_t)settings->width * settings->height * 3;
     DevBuf b_acc, b_out;
     DRB_CUDA(b_acc.alloc((size_t)W * H * 3 * sizeof(float), stream));

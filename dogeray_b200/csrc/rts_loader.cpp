@@ -580,6 +580,29 @@ int drb_host_scene_create(const drb_settings* settings, const drb_object* object
     return DRB_OK;
 }
 
+int64_t drb_host_scene_num_renderable(const drb_host_scene* hs)
+{
+    if (!hs) return 0;
+    if (hs->renderable >= 0) return hs->renderable;
+    const size_t n = hs->objects.size();
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() : 1, n / 65536 + 1));
+    std::vector<int64_t> part((size_t)nt, 0);
+    auto count = [&](int t) {
+        const size_t lo = n * (size_t)t / (size_t)nt, hi = n * ((size_t)t + 1) / (size_t)nt;
+        int64_t c = 0;
+        for (size_t i = lo; i < hi; ++i) c += drb_object_renderable(hs->objects[i]) ? 1 : 0;
+        part[(size_t)t] = c;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(count, t);
+    count(0);
+    for (auto& th : pool) th.join();
+    int64_t total = 0;
+    for (int64_t c : part) total += c;
+    hs->renderable = total;
+    return total;
+}
+
 void drb_host_scene_free(drb_host_scene* hs) { if (hs) { drb_host_scene_unpin(hs); delete hs; } }
 int64_t drb_host_scene_num_objects(const drb_host_scene* hs) { return hs ? (int64_t)hs->objects.size() : 0; }
 const drb_object* drb_host_scene_objects(const drb_host_scene* hs) { return hs && !hs->objects.empty() ? hs->objects.data() : nullptr; }

@@ -15,6 +15,7 @@
 #include "drb_internal.h"
 #include "device_scene.cuh"
 
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -24,18 +25,19 @@
 #include <mutex>
 #include <unordered_map>
 
+namespace cg = cooperative_groups;
+
 namespace {
 
-constexpr int kMaxTreeHeight = 96;      // traversal stack capacity in render.cu
+constexpr int kBuildThreads = 256;      // block size of the cooperative build kernels
 
-__host__ __device__ inline bool object_renderable(const drb_object& o)
-{
-    // same rule the loader reports with: SURVEY.md App. B.9 (types other than 0 / 2 are undefined
-    // behaviour in the reference) and junk lines that stop before the geometry columns
-    if (o.type == 2) return o.ncols == 0 || o.ncols >= 16;
-    if (o.type == 0) return o.ncols == 0 || o.ncols >= 10;
-    return false;
-}
+// what the host needs to know about a finished build, written by the build kernels and read back once
+struct BuildCtl {
+    int packed;                         // renderable objects k_pack saw (must equal the host scene's count)
+    int rounds, ploc_n, error;          // clustering rounds; clusters left; 1 = no progress, 2 = collapse overran
+    int nwide, wide_levels, stack_need; // four-wide nodes, their levels, exact bound of traversal pushes
+    int height;                         // height of the binary tree the nodes were emitted from
+};
 
 __device__ __forceinline__ int float_to_ordered(float f)
 {
@@ -55,7 +57,7 @@ __host__ __device__ __forceinline__ float ordered_to_float(int i)
 __global__ void k_flag(const drb_object* __restrict__ objs, int64_t n, int* __restrict__ flag)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = object_renderable(objs[i]) ? 1 : 0;
+    if (i < n) flag[i] = drb_object_renderable(objs[i]) ? 1 : 0;
 }
 
 __global__ void k_init_bounds(int* b)
@@ -65,13 +67,18 @@ __global__ void k_init_bounds(int* b)
 }
 
 // one thread per object line
-__global__ void k_pack(const drb_object* __restrict__ objs, int64_t n, const int* __restrict__ flag, const int* __restrict__ slot,
+__global__ void k_pack(const drb_object* __restrict__ objs, int64_t n, const int* __restrict__ flag, const int* __restrict__ slot, int nprims,
                        Prim* __restrict__ prims, ShadeRec* __restrict__ recs, int32_t* __restrict__ orig,
-                       float4* __restrict__ bmin, float4* __restrict__ bmax, int* __restrict__ scene_bounds)
+                       float4* __restrict__ bmin, float4* __restrict__ bmax, int* __restrict__ scene_bounds, int* __restrict__ packed)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
     bool live = i < n && flag[i];
+    // the arrays were sized from the host's count of renderable objects; the device counts too and the build fails if
+    // they disagree (never writes past the arrays)
+    const unsigned mlive = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && mlive) atomicAdd(packed, __popc(mlive));
+    if (live && slot[i] >= nprims) live = false;
     if (live) {
         const drb_object o = objs[i];
         const int k = slot[i];
@@ -281,69 +288,126 @@ __device__ __forceinline__ float union_half_area(const float4& alo, const float4
     return ex * ey + ey * ez + ez * ex;
 }
 
-__global__ void k_ploc_nn(int n, const float4* __restrict__ cmin, const float4* __restrict__ cmax, int32_t* __restrict__ nn)
+// block-wide exclusive scan of one 64-bit value per thread (two packed 32-bit counters); every thread also gets the block total
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long* total)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 lo = cmin[i], hi = cmax[i];
-    float best = 3.4e38f; int bj = -1;
-    const int j0 = max(0, i - kPlocRadius), j1 = min(n - 1, i + kPlocRadius);
-    for (int j = j0; j <= j1; ++j) {
-        if (j == i) continue;
-        const float a = union_half_area(lo, hi, cmin[j], cmax[j]);
-        if (a < best) { best = a; bj = j; }
+    __shared__ unsigned long long s_warp[kBuildThreads / 32];
+    __shared__ unsigned long long s_total;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= (unsigned)off) x += y;
     }
-    if (bj < 0) bj = (i ^ 1) < n ? (i ^ 1) : i - 1;        // non-finite boxes: pair neighbours so the loop still ends
-    nn[i] = bj;
-}
-
-// low word: cluster survives at this position; high word: it is the lower half of a merging pair
-__global__ void k_ploc_flag(int n, const int32_t* __restrict__ nn, unsigned long long* __restrict__ f)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int j = nn[i];
-    const bool mutual = j >= 0 && j < n && nn[j] == i;
-    const unsigned long long valid = !(mutual && i > j), merge = (mutual && i < j);
-    f[i] = valid | (merge << 32);
-}
-
-__global__ void k_ploc_emit(int n, const int32_t* __restrict__ nn, const unsigned long long* __restrict__ f, const unsigned long long* __restrict__ sc,
-                            const int32_t* __restrict__ cid, const float4* __restrict__ cmin, const float4* __restrict__ cmax,
-                            int32_t* __restrict__ cid_o, float4* __restrict__ cmin_o, float4* __restrict__ cmax_o, int node_base,
-                            int32_t* __restrict__ left, int32_t* __restrict__ right, float4* __restrict__ node_min, float4* __restrict__ node_max,
-                            int* __restrict__ totals)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long fi = f[i], si = sc[i];
-    if (i == n - 1) { totals[0] = (int)(uint32_t)si + (int)(fi & 1ull); totals[1] = (int)(si >> 32) + (int)(fi >> 32); }
-    if (!(fi & 1ull)) return;
-    const int pos = (int)(uint32_t)si;
-    if (fi >> 32) {
-        const int j = nn[i];
-        const int node = node_base + (int)(si >> 32);
-        const int a = cid[i], b = cid[j];
-        const float4 alo = cmin[i], ahi = cmax[i], blo = cmin[j], bhi = cmax[j];
-        const int ha = a < 0 ? 0 : __float_as_int(alo.w), hb = b < 0 ? 0 : __float_as_int(blo.w);
-        const float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float(max(ha, hb) + 1));
-        const float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
-        left[node] = a; right[node] = b;
-        node_min[node] = lo; node_max[node] = hi;
-        cid_o[pos] = node; cmin_o[pos] = lo; cmax_o[pos] = hi;
-    } else {
-        cid_o[pos] = cid[i]; cmin_o[pos] = cmin[i]; cmax_o[pos] = cmax[i];
+    __syncthreads();                                      // the previous call's readers are done with s_warp / s_total
+    if (lane == 31u) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = lane < kBuildThreads / 32 ? s_warp[lane] : 0ull;
+#pragma unroll
+        for (int off = 1; off < kBuildThreads / 32; off <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= (unsigned)off) w += y;
+        }
+        if (lane < kBuildThreads / 32) s_warp[lane] = w;              // inclusive over warps
+        if (lane == kBuildThreads / 32 - 1) s_total = w;
     }
+    __syncthreads();
+    *total = s_total;
+    return (x - v) + (warp ? s_warp[warp - 1] : 0ull);
 }
 
-__global__ void k_ploc_init(int n, const float4* __restrict__ lmin, const float4* __restrict__ lmax, int32_t* __restrict__ cid,
-                            float4* __restrict__ cmin, float4* __restrict__ cmax)
+// The whole clustering loop in ONE cooperative launch (it used to be four launches and a host read-back per round,
+// ~43 rounds for a million leaves).  Every block owns a contiguous chunk of the cluster array; a round is
+//   A  nearest neighbour of every cluster                                            | grid sync
+//   B  survive / merge flags, per-block totals                                       | grid sync
+//   C  positions and node ids from (prefix over block totals) + (scan inside block); emit the next cluster array;
+//      every block sums all block totals, so all agree on the next n without another exchange | grid sync
+// Positions and node ids are the same prefix sums the host mirror computes, so the topology is unchanged bit for bit.
+__global__ void __launch_bounds__(kBuildThreads) k_ploc_all(int n0, const float4* __restrict__ lmin, const float4* __restrict__ lmax,
+                                                            int32_t* cid0, int32_t* cid1, float4* cmn0, float4* cmn1, float4* cmx0, float4* cmx1,
+                                                            int32_t* nn, unsigned long long* f, unsigned long long* blk_tot,
+                                                            int32_t* left, int32_t* right, float4* node_min, float4* node_max, BuildCtl* ctl)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    cid[i] = ~i;
-    float4 lo = lmin[i]; lo.w = 0.f;
-    cmin[i] = lo; cmax[i] = lmax[i];
+    cg::grid_group grid = cg::this_grid();
+    const int nb = (int)gridDim.x, b = (int)blockIdx.x, t = (int)threadIdx.x;
+    int32_t* cid[2] = { cid0, cid1 }; float4* cmn[2] = { cmn0, cmn1 }; float4* cmx[2] = { cmx0, cmx1 };
+    for (int i = b * kBuildThreads + t; i < n0; i += nb * kBuildThreads) {
+        cid0[i] = ~i;
+        float4 lo = lmin[i]; lo.w = 0.f;
+        cmn0[i] = lo; cmx0[i] = lmax[i];
+    }
+    grid.sync();
+    int n = n0, node_base = 0, cur = 0, rounds = 0, err = 0;
+    while (n > 1) {
+        const int chunk = max((n + nb - 1) / nb, kBuildThreads);
+        const int c0 = min(n, b * chunk), c1 = min(n, c0 + chunk);
+        const float4* cmin = cmn[cur]; const float4* cmax = cmx[cur];
+        // A
+        for (int i = c0 + t; i < c1; i += kBuildThreads) {
+            const float4 lo = cmin[i], hi = cmax[i];
+            float best = 3.4e38f; int bj = -1;
+            const int j0 = max(0, i - kPlocRadius), j1 = min(n - 1, i + kPlocRadius);
+            for (int j = j0; j <= j1; ++j) {
+                if (j == i) continue;
+                const float a = union_half_area(lo, hi, cmin[j], cmax[j]);
+                if (a < best) { best = a; bj = j; }
+            }
+            if (bj < 0) bj = (i ^ 1) < n ? (i ^ 1) : i - 1;        // non-finite boxes: pair neighbours so the loop still ends
+            nn[i] = bj;
+        }
+        grid.sync();
+        // B: low word = the cluster survives at this position, high word = it is the lower half of a merging pair
+        unsigned long long mine = 0ull;
+        for (int i = c0 + t; i < c1; i += kBuildThreads) {
+            const int j = nn[i];
+            const bool mutual = j >= 0 && j < n && nn[j] == i;
+            const unsigned long long valid = !(mutual && i > j), merge = (mutual && i < j);
+            const unsigned long long fi = valid | (merge << 32);
+            f[i] = fi;
+            mine += fi;
+        }
+        unsigned long long tot;
+        block_excl_scan(mine, &tot);
+        if (t == 0) blk_tot[b] = tot;
+        grid.sync();
+        // C
+        unsigned long long before = 0ull, all = 0ull;
+        for (int k = t; k < nb; k += kBuildThreads) { const unsigned long long v = blk_tot[k]; all += v; if (k < b) before += v; }
+        { unsigned long long sum; block_excl_scan(all, &sum); all = sum; block_excl_scan(before, &sum); before = sum; }
+        unsigned long long running = before;
+        for (int base = c0; base < c1; base += kBuildThreads) {
+            const int i = base + t;
+            const unsigned long long fi = i < c1 ? f[i] : 0ull;
+            unsigned long long tile;
+            const unsigned long long si = running + block_excl_scan(fi, &tile);
+            running += tile;
+            if (fi & 1ull) {
+                const int pos = (int)(uint32_t)si;
+                if (fi >> 32) {
+                    const int j = nn[i];
+                    const int node = node_base + (int)(si >> 32);
+                    const int a = cid[cur][i], bb = cid[cur][j];
+                    const float4 alo = cmin[i], ahi = cmax[i], blo = cmin[j], bhi = cmax[j];
+                    const int ha = a < 0 ? 0 : __float_as_int(alo.w), hb = bb < 0 ? 0 : __float_as_int(blo.w);
+                    const float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float(max(ha, hb) + 1));
+                    const float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+                    left[node] = a; right[node] = bb;
+                    node_min[node] = lo; node_max[node] = hi;
+                    cid[cur ^ 1][pos] = node; cmn[cur ^ 1][pos] = lo; cmx[cur ^ 1][pos] = hi;
+                } else {
+                    cid[cur ^ 1][pos] = cid[cur][i]; cmn[cur ^ 1][pos] = cmin[i]; cmx[cur ^ 1][pos] = cmax[i];
+                }
+            }
+        }
+        const int survivors = (int)(uint32_t)all, merges = (int)(all >> 32);
+        ++rounds;
+        if (merges <= 0 || survivors != n - merges) { err = 1; break; }          // same totals in every block: all leave together
+        node_base += merges; n = survivors; cur ^= 1;
+        grid.sync();
+    }
+    if (b == 0 && t == 0) { ctl->rounds = rounds; ctl->error = err; ctl->ploc_n = n; }
 }
 
 // both planes of one axis of a child box -> min_q | max_q << 16, rounded outwards + 1 quantum
@@ -391,61 +455,121 @@ __device__ __forceinline__ float box_half_area(const float4& lo, const float4& h
     return ex * ey + ey * ez + ez * ex;
 }
 
-__global__ void k_wide_expand(int nq, const int32_t* __restrict__ queue, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
-                              const float4* __restrict__ node_min, const float4* __restrict__ node_max, int4* __restrict__ slots, int* __restrict__ counts)
+// The breadth-first collapse in ONE cooperative launch (was: three launches and a host read-back per level).  Per level
+//   A  expand every queued binary node into up to four slots, count its internal children, per-block totals | grid sync
+//   B  child ids from (prefix over block totals) + (scan inside the block); emit the wide nodes and the next queue | grid sync
+// and afterwards, bottom-up over the recorded levels, the exact stack bound of the traversal kernel: visiting a node
+// pushes all but one of its children, so need(node) = (children - 1) + max over internal children of need(child).
+constexpr int kMaxWideLevels = 512;
+__global__ void __launch_bounds__(kBuildThreads) k_wide_all(const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                            const float4* __restrict__ node_min, const float4* __restrict__ node_max,
+                                                            const float4* __restrict__ lmin, const float4* __restrict__ lmax,
+                                                            const int* __restrict__ scene_bounds, int max_nodes,
+                                                            int32_t* wq0, int32_t* wq1, int4* slots, int* counts, unsigned long long* blk_tot,
+                                                            WideNode* out, int* need, BuildCtl* ctl)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const int b = queue[i];
-    int s[4] = { left[b], right[b], DRB_WIDE_EMPTY, DRB_WIDE_EMPTY };
-    int n = 2;
-    for (int it = 0; it < 2; ++it) {
-        int pick = -1; float best = -1.0f;
-        for (int k = 0; k < n; ++k)
-            if (s[k] >= 0) {
-                const float a = box_half_area(node_min[s[k]], node_max[s[k]]);
-                if (a > best) { best = a; pick = k; }
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_level_start[kMaxWideLevels + 1];
+    const int nb = (int)gridDim.x, b = (int)blockIdx.x, t = (int)threadIdx.x;
+    int32_t* wq[2] = { wq0, wq1 };
+    if (b == 0 && t == 0) wq0[0] = 0;                               // level 0 = { binary root 0 }
+    grid.sync();
+    int nq = 1, level_base = 0, cur = 0, levels = 0, err = 0;
+    while (nq > 0) {
+        if (levels >= kMaxWideLevels || level_base + nq > max_nodes) { err = 2; break; }
+        if (t == 0) s_level_start[levels] = level_base;
+        const int chunk = max((nq + nb - 1) / nb, kBuildThreads);
+        const int c0 = min(nq, b * chunk), c1 = min(nq, c0 + chunk);
+        // A
+        unsigned long long mine = 0ull;
+        for (int i = c0 + t; i < c1; i += kBuildThreads) {
+            const int bn = wq[cur][i];
+            int s[4] = { left[bn], right[bn], DRB_WIDE_EMPTY, DRB_WIDE_EMPTY };
+            int n = 2;
+            for (int it = 0; it < 2; ++it) {
+                int pick = -1; float best = -1.0f;
+                for (int k = 0; k < n; ++k)
+                    if (s[k] >= 0) {
+                        const float a = box_half_area(node_min[s[k]], node_max[s[k]]);
+                        if (a > best) { best = a; pick = k; }
+                    }
+                if (pick < 0) break;
+                const int c = s[pick];
+                s[pick] = left[c];
+                s[n++] = right[c];
             }
-        if (pick < 0) break;
-        const int c = s[pick];
-        s[pick] = left[c];
-        s[n++] = right[c];
-    }
-    int internal = 0;
-    for (int k = 0; k < 4; ++k) internal += (s[k] >= 0) ? 1 : 0;
-    slots[i] = make_int4(s[0], s[1], s[2], s[3]);
-    counts[i] = internal;
-}
-
-__global__ void k_wide_emit(int nq, int level_base, int next_base, const int4* __restrict__ slots, const int* __restrict__ counts,
-                            const int* __restrict__ offsets, const float4* __restrict__ lmin, const float4* __restrict__ lmax,
-                            const float4* __restrict__ node_min, const float4* __restrict__ node_max, const int* __restrict__ scene_bounds,
-                            WideNode* __restrict__ out, int32_t* __restrict__ next_queue, int* __restrict__ total)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const int4 s4 = slots[i];
-    const int s[4] = { s4.x, s4.y, s4.z, s4.w };
-    const int off = offsets[i];
-    if (i == nq - 1) *total = off + counts[i];
-    WideNode nd;
-    int j = 0;
+            int internal = 0;
+            for (int k = 0; k < 4; ++k) internal += (s[k] >= 0) ? 1 : 0;
+            slots[i] = make_int4(s[0], s[1], s[2], s[3]);
+            counts[i] = internal;
+            mine += (unsigned long long)internal;
+        }
+        unsigned long long tot;
+        block_excl_scan(mine, &tot);
+        if (t == 0) blk_tot[b] = tot;
+        grid.sync();
+        // B
+        unsigned long long before = 0ull, all = 0ull;
+        for (int k = t; k < nb; k += kBuildThreads) { const unsigned long long v = blk_tot[k]; all += v; if (k < b) before += v; }
+        { unsigned long long sum; block_excl_scan(all, &sum); all = sum; block_excl_scan(before, &sum); before = sum; }
+        const int next_base = level_base + nq;
+        unsigned long long running = before;
+        for (int base = c0; base < c1; base += kBuildThreads) {
+            const int i = base + t;
+            const unsigned long long ci = i < c1 ? (unsigned long long)counts[i] : 0ull;
+            unsigned long long tile;
+            const int off = (int)(running + block_excl_scan(ci, &tile));
+            running += tile;
+            if (i < c1) {
+                const int4 s4 = slots[i];
+                const int s[4] = { s4.x, s4.y, s4.z, s4.w };
+                WideNode nd;
+                int j = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        uint32_t q[3] = { 0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu };          // min 65535 > max 0: never hit
-        int link = DRB_WIDE_EMPTY;
-        if (s[k] != DRB_WIDE_EMPTY) {
-            if (s[k] < 0) { quant_child(lmin[~s[k]], lmax[~s[k]], scene_bounds, q); link = s[k]; }
-            else {
-                quant_child(node_min[s[k]], node_max[s[k]], scene_bounds, q);
-                link = next_base + off + j;
-                next_queue[off + j] = s[k];
-                ++j;
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t q[3] = { 0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu };          // min 65535 > max 0: never hit
+                    int link = DRB_WIDE_EMPTY;
+                    if (s[k] != DRB_WIDE_EMPTY) {
+                        if (s[k] < 0) { quant_child(lmin[~s[k]], lmax[~s[k]], scene_bounds, q); link = s[k]; }
+                        else {
+                            quant_child(node_min[s[k]], node_max[s[k]], scene_bounds, q);
+                            link = next_base + off + j;
+                            wq[cur ^ 1][off + j] = s[k];
+                            ++j;
+                        }
+                    }
+                    nd.bx[k] = q[0]; nd.by[k] = q[1]; nd.bz[k] = q[2]; nd.child[k] = link;
+                }
+                out[level_base + i] = nd;
             }
         }
-        nd.bx[k] = q[0]; nd.by[k] = q[1]; nd.bz[k] = q[2]; nd.child[k] = link;
+        level_base += nq; nq = (int)all; cur ^= 1; ++levels;
+        grid.sync();
     }
-    out[level_base + i] = nd;
+    if (t == 0) s_level_start[min(levels, kMaxWideLevels)] = level_base;
+    __syncthreads();
+    // exact stack bound, deepest level first (children live on the next level, so they are done)
+    if (!err)
+        for (int L = levels - 1; L >= 0; --L) {
+            const int l0 = s_level_start[L], l1 = s_level_start[L + 1];
+            for (int i = l0 + b * kBuildThreads + t; i < l1; i += nb * kBuildThreads) {
+                int kids = 0, deepest = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = out[i].child[k];
+                    if (c == DRB_WIDE_EMPTY) continue;
+                    ++kids;
+                    if (c >= 0) deepest = max(deepest, need[c]);
+                }
+                need[i] = max(kids - 1, 0) + deepest;
+            }
+            grid.sync();
+        }
+    if (b == 0 && t == 0) {
+        ctl->nwide = level_base; ctl->wide_levels = levels; ctl->stack_need = err ? 0 : need[0];
+        ctl->height = __float_as_int(node_min[0].w);
+        if (err) ctl->error = err;
+    }
 }
 
 __global__ void k_wide_single(const float4* __restrict__ lmin, const float4* __restrict__ lmax, const int* __restrict__ scene_bounds, WideNode* __restrict__ out)
@@ -487,7 +611,7 @@ struct BlockCache {
     std::unordered_map<void*, size_t> live;                     // every block handed out -> its size
     std::unordered_map<int, std::unordered_multimap<size_t, void*>> idle;   // device -> (size -> idle blocks)
     std::unordered_map<int, size_t> idle_bytes;
-    static constexpr size_t kMaxIdleBytes = size_t(48) << 30;   // beyond this, blocks go back to the pool
+    static constexpr size_t kMaxIdleBytes = size_t(48) << 30;   // beyond this, blocks go back to the pool (and all of them do when an allocation fails)
 } g_cache;
 }
 
@@ -509,6 +633,21 @@ cudaError_t drb_dev_alloc(void** p, size_t bytes, cudaStream_t st)
         }
     }
     cudaError_t e = cudaMallocAsync(p, bytes, st);
+    if (e == cudaErrorMemoryAllocation) {
+        // idle blocks of other sizes may be holding the memory: give them back to the pool and try once more
+        cudaGetLastError();
+        std::vector<void*> blocks;
+        {
+            std::lock_guard<std::mutex> g(g_cache.mu);
+            for (auto& kv : g_cache.idle[dev]) blocks.push_back(kv.second);
+            g_cache.idle[dev].clear();
+            g_cache.idle_bytes[dev] = 0;
+        }
+        if (!blocks.empty()) {
+            for (void* b : blocks) cudaFreeAsync(b, st);       // idle blocks are not in use by any stream
+            e = cudaMallocAsync(p, bytes, st);
+        }
+    }
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> g(g_cache.mu);
     g_cache.live[*p] = bytes;
@@ -564,39 +703,62 @@ int retain_pool(int device)
     return DRB_OK;
 }
 
-int build_tree(drb_scene* s, const drb_host_scene* hs)
+struct EventTrio {
+    cudaEvent_t e[3] = { nullptr, nullptr, nullptr };
+    ~EventTrio() { for (auto x : e) if (x) cudaEventDestroy(x); }
+    int create() { for (auto& x : e) DRB_CUDA(cudaEventCreate(&x)); return DRB_OK; }
+};
+
+// co-resident grid of a cooperative build kernel, asked once per process and device
+int coop_grid(int device, const void* kernel, int want_blocks, int* blocks)
+{
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, int> cache;
+    std::lock_guard<std::mutex> g(mu);
+    const uint64_t key = ((uint64_t)(uintptr_t)kernel << 8) ^ (uint64_t)(device & 0xFF);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int sms = 148, per_sm = 1;
+        DRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBuildThreads, 0));
+        it = cache.emplace(key, sms * std::max(std::min(per_sm, 4), 1)).first;
+    }
+    *blocks = std::max(1, std::min(it->second, want_blocks));
+    return DRB_OK;
+}
+
+// Upload (unless the object lines are already on the device) + the whole tree build, enqueued on the scene's stream with
+// ONE host synchronisation at the end: the number of renderable objects is known on the host (drb_host_scene counts
+// them once), and both data-dependent loops -- clustering rounds, collapse levels -- run inside cooperative kernels.
+int build_tree(drb_scene* s, const drb_host_scene* hs, const drb_object* objs_dev)
 {
     const int64_t nobj = (int64_t)hs->objects.size();
     if (nobj >= (1ll << 31) - 8) { drb_set_error("too many objects (%lld)", (long long)nobj); return DRB_ERR_UNSUPPORTED; }
     cudaStream_t st = s->stream;
     Scratch tmp(st);
-    cudaEvent_t e0, e1, e2;
-    DRB_CUDA(cudaEventCreate(&e0)); DRB_CUDA(cudaEventCreate(&e1)); DRB_CUDA(cudaEventCreate(&e2));
-    DRB_CUDA(cudaEventRecord(e0, st));
+    EventTrio ev;
+    if (int rc = ev.create()) return rc;
+    DRB_CUDA(cudaEventRecord(ev.e[0], st));
 
-    drb_object* d_objs = nullptr; int* d_flag = nullptr; int* d_slot = nullptr; int* d_bounds = nullptr;
-    if (int rc = tmp.alloc(&d_objs, (size_t)nobj)) return rc;
+    const bool keep = (s->build_flags & DRB_BUILD_KEEP_DEBUG) != 0;
+    const bool lbvh_only = (s->build_flags & DRB_BUILD_LBVH_ONLY) != 0;
+    const int nprims = (int)drb_host_scene_num_renderable(hs);
+    const drb_object* d_objs = objs_dev;
+    int* d_flag = nullptr; int* d_slot = nullptr; int* d_bounds = nullptr; BuildCtl* d_ctl = nullptr;
+    if (!d_objs) {
+        drb_object* up = nullptr;
+        if (int rc = tmp.alloc(&up, (size_t)nobj)) return rc;
+        if (nobj) DRB_CUDA(cudaMemcpyAsync(up, hs->objects.data(), (size_t)nobj * sizeof(drb_object), cudaMemcpyHostToDevice, st));
+        d_objs = up;
+    }
     if (int rc = tmp.alloc(&d_flag, (size_t)nobj + 1)) return rc;
     if (int rc = tmp.alloc(&d_slot, (size_t)nobj + 1)) return rc;
     if (int rc = tmp.alloc(&d_bounds, 8)) return rc;
-    if (nobj) DRB_CUDA(cudaMemcpyAsync(d_objs, hs->objects.data(), (size_t)nobj * sizeof(drb_object), cudaMemcpyHostToDevice, st));
-    DRB_CUDA(cudaEventRecord(e1, st));
+    if (int rc = tmp.alloc(&d_ctl, 1)) return rc;
+    DRB_CUDA(cudaMemsetAsync(d_ctl, 0, sizeof(BuildCtl), st));
+    DRB_CUDA(cudaEventRecord(ev.e[1], st));
 
     const int T = 256;
-    int nprims = 0;
-    if (nobj) {
-        k_flag<<<(unsigned)((nobj + T - 1) / T), T, 0, st>>>(d_objs, nobj, d_flag);
-        size_t scan_bytes = 0;
-        DRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag, d_slot, (int)nobj, st));
-        void* d_scan = nullptr;
-        if (int rc = tmp.alloc((char**)&d_scan, scan_bytes)) return rc;
-        DRB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_flag, d_slot, (int)nobj, st));
-        int last_slot = 0, last_flag = 0;
-        DRB_CUDA(cudaMemcpyAsync(&last_slot, d_slot + nobj - 1, 4, cudaMemcpyDeviceToHost, st));
-        DRB_CUDA(cudaMemcpyAsync(&last_flag, d_flag + nobj - 1, 4, cudaMemcpyDeviceToHost, st));
-        DRB_CUDA(cudaStreamSynchronize(st));
-        nprims = last_slot + last_flag;
-    }
     s->nobjects = nobj;
     s->nprims = nprims;
     s->nnodes = nprims == 0 ? 0 : std::max(1, nprims - 1);
@@ -607,22 +769,30 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
     if (int rc = dev_alloc(&s->recs, (size_t)nprims, st)) return rc;
     if (int rc = dev_alloc(&s->orig_id, (size_t)nprims, st)) return rc;
     const size_t nint = nprims > 1 ? (size_t)nprims - 1 : 1;
-    if (int rc = dev_alloc(&s->dbg.keys, (size_t)nprims, st)) return rc;
-    if (int rc = dev_alloc(&s->dbg.order, (size_t)nprims, st)) return rc;
-    if (int rc = dev_alloc(&s->dbg.parent, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->dbg.left, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->dbg.right, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->dbg.node_min, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->dbg.node_max, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->tree.left, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->tree.right, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->tree.node_min, nint, st)) return rc;
-    if (int rc = dev_alloc(&s->tree.node_max, nint, st)) return rc;
+    // the integer outputs of the build stay resident only on request (drb_scene_lbvh / drb_scene_tree); otherwise they
+    // are scratch: ~100 B per primitive that rendering never reads
+    auto side = [&](auto** p, size_t count) -> int { return keep ? dev_alloc(p, count, st) : tmp.alloc(p, count); };
+    LbvhDebug dbg; FinalTree tree;
+    if (int rc = side(&dbg.keys, (size_t)nprims)) return rc;
+    if (int rc = side(&dbg.order, (size_t)nprims)) return rc;
+    if (keep || lbvh_only) {
+        if (int rc = side(&dbg.parent, nint)) return rc;
+        if (int rc = side(&dbg.left, nint)) return rc;
+        if (int rc = side(&dbg.right, nint)) return rc;
+        if (int rc = side(&dbg.node_min, nint)) return rc;
+        if (int rc = side(&dbg.node_max, nint)) return rc;
+    }
+    if (int rc = side(&tree.left, nint)) return rc;
+    if (int rc = side(&tree.right, nint)) return rc;
+    if (int rc = side(&tree.node_min, nint)) return rc;
+    if (int rc = side(&tree.node_max, nint)) return rc;
+    if (keep) { s->dbg = dbg; s->tree = tree; }
 
-    int height = 0;
+    BuildCtl ctl; memset(&ctl, 0, sizeof ctl);
+    int hb[6] = { 0, 0, 0, 0, 0, 0 };
     if (nprims > 0) {
         Prim* prims_u; ShadeRec* recs_u; int32_t* orig_u; float4 *bmin_u, *bmax_u, *lmin, *lmax;
-        uint64_t* keys_u; int32_t* idx_u; int32_t* leaf_parent; int* visits; int* d_height;
+        uint64_t* keys_u; int32_t* idx_u;
         if (int rc = tmp.alloc(&prims_u, (size_t)nprims)) return rc;
         if (int rc = tmp.alloc(&recs_u, (size_t)nprims)) return rc;
         if (int rc = tmp.alloc(&orig_u, (size_t)nprims)) return rc;
@@ -632,38 +802,48 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
         if (int rc = tmp.alloc(&lmax, (size_t)nprims)) return rc;
         if (int rc = tmp.alloc(&keys_u, (size_t)nprims)) return rc;
         if (int rc = tmp.alloc(&idx_u, (size_t)nprims)) return rc;
-        if (int rc = tmp.alloc(&leaf_parent, (size_t)nprims)) return rc;
-        if (int rc = tmp.alloc(&visits, nint)) return rc;
-        if (int rc = tmp.alloc(&d_height, 1)) return rc;
 
+        k_flag<<<(unsigned)((nobj + T - 1) / T), T, 0, st>>>(d_objs, nobj, d_flag);
+        size_t scan_bytes = 0;
+        DRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag, d_slot, (int)nobj, st));
+        void* d_scan = nullptr;
+        if (int rc = tmp.alloc((char**)&d_scan, scan_bytes)) return rc;
+        DRB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_flag, d_slot, (int)nobj, st));
         k_init_bounds<<<1, 32, 0, st>>>(d_bounds);
-        k_pack<<<(unsigned)((nobj + T - 1) / T), T, 0, st>>>(d_objs, nobj, d_flag, d_slot, prims_u, recs_u, orig_u, bmin_u, bmax_u, d_bounds);
+        k_pack<<<(unsigned)((nobj + T - 1) / T), T, 0, st>>>(d_objs, nobj, d_flag, d_slot, nprims, prims_u, recs_u, orig_u, bmin_u, bmax_u, d_bounds, &d_ctl->packed);
         k_keys<<<(nprims + T - 1) / T, T, 0, st>>>(bmin_u, bmax_u, nprims, d_bounds, keys_u, idx_u);
         size_t sort_bytes = 0;
-        DRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_u, s->dbg.keys, idx_u, s->dbg.order, nprims, 0, 63, st));
+        DRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_u, dbg.keys, idx_u, dbg.order, nprims, 0, 63, st));
         void* d_sort = nullptr;
         if (int rc = tmp.alloc((char**)&d_sort, sort_bytes)) return rc;
-        DRB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_u, s->dbg.keys, idx_u, s->dbg.order, nprims, 0, 63, st));
+        DRB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, keys_u, dbg.keys, idx_u, dbg.order, nprims, 0, 63, st));
         {
             const long long threads = (long long)nprims * 8;
-            k_gather<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(s->dbg.order, nprims, prims_u, recs_u, orig_u, bmin_u, bmax_u,
+            k_gather<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(dbg.order, nprims, prims_u, recs_u, orig_u, bmin_u, bmax_u,
                                                                       s->prims, s->recs, s->orig_id, lmin, lmax);
         }
+        if (int rc = dev_alloc(&s->wnodes, nint, st)) return rc;
         if (nprims > 1) {
-            DRB_CUDA(cudaMemsetAsync(visits, 0, nint * sizeof(int), st));
-            DRB_CUDA(cudaMemsetAsync(d_height, 0, sizeof(int), st));
-            k_karras<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(s->dbg.keys, nprims, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent);
-            k_refit<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, s->dbg.left, s->dbg.right, s->dbg.parent, leaf_parent, visits,
-                                                       s->dbg.node_min, s->dbg.node_max, d_height);
-            if (s->build_flags & DRB_BUILD_LBVH_ONLY) {
-                DRB_CUDA(cudaMemcpyAsync(s->tree.left, s->dbg.left, nint * 4, cudaMemcpyDeviceToDevice, st));
-                DRB_CUDA(cudaMemcpyAsync(s->tree.right, s->dbg.right, nint * 4, cudaMemcpyDeviceToDevice, st));
-                DRB_CUDA(cudaMemcpyAsync(s->tree.node_min, s->dbg.node_min, nint * 16, cudaMemcpyDeviceToDevice, st));
-                DRB_CUDA(cudaMemcpyAsync(s->tree.node_max, s->dbg.node_max, nint * 16, cudaMemcpyDeviceToDevice, st));
-                DRB_CUDA(cudaMemcpyAsync(&height, d_height, 4, cudaMemcpyDeviceToHost, st));
+            if (keep || lbvh_only) {
+                // the LBVH of north_star: Karras hierarchy + bottom-up refit (the traversal tree only with DRB_BUILD_LBVH_ONLY)
+                int32_t* leaf_parent; int* visits; int* d_height;
+                if (int rc = tmp.alloc(&leaf_parent, (size_t)nprims)) return rc;
+                if (int rc = tmp.alloc(&visits, nint)) return rc;
+                if (int rc = tmp.alloc(&d_height, 1)) return rc;
+                DRB_CUDA(cudaMemsetAsync(visits, 0, nint * sizeof(int), st));
+                DRB_CUDA(cudaMemsetAsync(d_height, 0, sizeof(int), st));
+                k_karras<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(dbg.keys, nprims, dbg.left, dbg.right, dbg.parent, leaf_parent);
+                k_refit<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, dbg.left, dbg.right, dbg.parent, leaf_parent, visits,
+                                                           dbg.node_min, dbg.node_max, d_height);
+            }
+            if (lbvh_only) {
+                DRB_CUDA(cudaMemcpyAsync(tree.left, dbg.left, nint * 4, cudaMemcpyDeviceToDevice, st));
+                DRB_CUDA(cudaMemcpyAsync(tree.right, dbg.right, nint * 4, cudaMemcpyDeviceToDevice, st));
+                DRB_CUDA(cudaMemcpyAsync(tree.node_min, dbg.node_min, nint * 16, cudaMemcpyDeviceToDevice, st));
+                DRB_CUDA(cudaMemcpyAsync(tree.node_max, dbg.node_max, nint * 16, cudaMemcpyDeviceToDevice, st));
             } else {
                 // SAH-guided rebuild over the same sorted leaves
-                int32_t* cid[2]; float4* cmn[2]; float4* cmx[2]; int32_t* nn; unsigned long long *fl, *sc; int* d_tot;
+                int32_t* cid[2]; float4* cmn[2]; float4* cmx[2]; int32_t* nn; unsigned long long *fl, *btot;
                 int32_t *pl, *pr; float4 *pmin, *pmax;
                 for (int k = 0; k < 2; ++k) {
                     if (int rc = tmp.alloc(&cid[k], (size_t)nprims)) return rc;
@@ -672,93 +852,60 @@ int build_tree(drb_scene* s, const drb_host_scene* hs)
                 }
                 if (int rc = tmp.alloc(&nn, (size_t)nprims)) return rc;
                 if (int rc = tmp.alloc(&fl, (size_t)nprims)) return rc;
-                if (int rc = tmp.alloc(&sc, (size_t)nprims)) return rc;
-                if (int rc = tmp.alloc(&d_tot, 2)) return rc;
                 if (int rc = tmp.alloc(&pl, nint)) return rc;
                 if (int rc = tmp.alloc(&pr, nint)) return rc;
                 if (int rc = tmp.alloc(&pmin, nint)) return rc;
                 if (int rc = tmp.alloc(&pmax, nint)) return rc;
-                size_t pscan_bytes = 0;
-                DRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, pscan_bytes, fl, sc, nprims, st));
-                void* d_pscan = nullptr;
-                if (int rc = tmp.alloc((char**)&d_pscan, pscan_bytes)) return rc;
-                k_ploc_init<<<(nprims + T - 1) / T, T, 0, st>>>(nprims, lmin, lmax, cid[0], cmn[0], cmx[0]);
-                int n = nprims, node_base = 0, cur = 0, iters = 0;
-                while (n > 1) {
-                    const int g = (n + T - 1) / T;
-                    k_ploc_nn<<<g, T, 0, st>>>(n, cmn[cur], cmx[cur], nn);
-                    k_ploc_flag<<<g, T, 0, st>>>(n, nn, fl);
-                    DRB_CUDA(cub::DeviceScan::ExclusiveSum(d_pscan, pscan_bytes, fl, sc, n, st));
-                    k_ploc_emit<<<g, T, 0, st>>>(n, nn, fl, sc, cid[cur], cmn[cur], cmx[cur], cid[cur ^ 1], cmn[cur ^ 1], cmx[cur ^ 1], node_base,
-                                                 pl, pr, pmin, pmax, d_tot);
-                    int tot[2] = { 0, 0 };
-                    DRB_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
-                    DRB_CUDA(cudaStreamSynchronize(st));
-                    if (tot[1] <= 0 || tot[0] != n - tot[1] || ++iters > 100000) { drb_set_error("hierarchy rebuild made no progress (n=%d, merges=%d)", n, tot[1]); return DRB_ERR_CUDA; }
-                    node_base += tot[1]; n = tot[0]; cur ^= 1;
-                }
-                s->info.rebuild_iterations = iters;
-                k_relabel<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, pl, pr, pmin, pmax, s->tree.left, s->tree.right,
-                                                                          s->tree.node_min, s->tree.node_max);
-                float4 rootbox;
-                DRB_CUDA(cudaMemcpyAsync(&rootbox, pmin + (nprims - 2), sizeof rootbox, cudaMemcpyDeviceToHost, st));
-                DRB_CUDA(cudaStreamSynchronize(st));
-                memcpy(&height, &rootbox.w, 4);
+                int blocks = 1;
+                if (int rc = coop_grid(s->device, (const void*)k_ploc_all, (nprims + kBuildThreads - 1) / kBuildThreads, &blocks)) return rc;
+                if (int rc = tmp.alloc(&btot, (size_t)blocks)) return rc;
+                int n0 = nprims;
+                const float4* c_lmin = lmin; const float4* c_lmax = lmax;
+                void* args[] = { &n0, &c_lmin, &c_lmax, &cid[0], &cid[1], &cmn[0], &cmn[1], &cmx[0], &cmx[1], &nn, &fl, &btot, &pl, &pr, &pmin, &pmax, &d_ctl };
+                DRB_CUDA(cudaLaunchCooperativeKernel((const void*)k_ploc_all, dim3(blocks), dim3(kBuildThreads), args, 0, st));
+                k_relabel<<<(nprims - 1 + T - 1) / T, T, 0, st>>>(nprims, pl, pr, pmin, pmax, tree.left, tree.right, tree.node_min, tree.node_max);
             }
-        } else {
-            height = 1;
-        }
-        // ---- four-wide collapse of the final tree (s->tree.*, root 0)
-        if (int rc = dev_alloc(&s->wnodes, nint, st)) return rc;
-        if (nprims > 1) {
-            int32_t* wq[2]; int4* wslots; int *wcounts, *woffs, *wtotal;
+            // ---- four-wide collapse of the final tree (tree.*, root 0)
+            int32_t* wq[2]; int4* wslots; int *wcounts, *wneed; unsigned long long* wtot;
             if (int rc = tmp.alloc(&wq[0], (size_t)nprims)) return rc;
             if (int rc = tmp.alloc(&wq[1], (size_t)nprims)) return rc;
             if (int rc = tmp.alloc(&wslots, (size_t)nprims)) return rc;
             if (int rc = tmp.alloc(&wcounts, (size_t)nprims)) return rc;
-            if (int rc = tmp.alloc(&woffs, (size_t)nprims)) return rc;
-            if (int rc = tmp.alloc(&wtotal, 1)) return rc;
-            size_t wscan_bytes = 0;
-            DRB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, wscan_bytes, wcounts, woffs, nprims, st));
-            void* d_wscan = nullptr;
-            if (int rc = tmp.alloc((char**)&d_wscan, wscan_bytes)) return rc;
-            DRB_CUDA(cudaMemsetAsync(wq[0], 0, sizeof(int32_t), st));        // level 0 = { binary root 0 }
-            int nq = 1, level_base = 0, cur = 0, levels = 0;
-            while (nq > 0) {
-                const int g = (nq + T - 1) / T;
-                k_wide_expand<<<g, T, 0, st>>>(nq, wq[cur], s->tree.left, s->tree.right, s->tree.node_min, s->tree.node_max, wslots, wcounts);
-                DRB_CUDA(cub::DeviceScan::ExclusiveSum(d_wscan, wscan_bytes, wcounts, woffs, nq, st));
-                k_wide_emit<<<g, T, 0, st>>>(nq, level_base, level_base + nq, wslots, wcounts, woffs, lmin, lmax, s->tree.node_min, s->tree.node_max,
-                                             d_bounds, s->wnodes, wq[cur ^ 1], wtotal);
-                int tot = 0;
-                DRB_CUDA(cudaMemcpyAsync(&tot, wtotal, sizeof tot, cudaMemcpyDeviceToHost, st));
-                DRB_CUDA(cudaStreamSynchronize(st));
-                level_base += nq; nq = tot; cur ^= 1; ++levels;
-                if (levels > 4096 || level_base + nq > (int)nint) { drb_set_error("wide collapse overran (%d nodes, level %d)", level_base + nq, levels); return DRB_ERR_CUDA; }
-            }
-            s->nwnodes = level_base; s->wide_levels = levels;
+            if (int rc = tmp.alloc(&wneed, nint)) return rc;
+            int blocks = 1;
+            if (int rc = coop_grid(s->device, (const void*)k_wide_all, (nprims / 2 + kBuildThreads - 1) / kBuildThreads, &blocks)) return rc;
+            if (int rc = tmp.alloc(&wtot, (size_t)blocks)) return rc;
+            const int32_t* c_left = tree.left; const int32_t* c_right = tree.right; const float4* c_nmin = tree.node_min; const float4* c_nmax = tree.node_max;
+            const float4* c_lmin = lmin; const float4* c_lmax = lmax; const int* c_bounds = d_bounds;
+            int max_nodes = (int)nint;
+            void* args[] = { &c_left, &c_right, &c_nmin, &c_nmax, &c_lmin, &c_lmax, &c_bounds, &max_nodes, &wq[0], &wq[1], &wslots, &wcounts, &wtot,
+                             &s->wnodes, &wneed, &d_ctl };
+            DRB_CUDA(cudaLaunchCooperativeKernel((const void*)k_wide_all, dim3(blocks), dim3(kBuildThreads), args, 0, st));
         } else {
             k_wide_single<<<1, 1, 0, st>>>(lmin, lmax, d_bounds, s->wnodes);
-            s->nwnodes = 1; s->wide_levels = 1;
         }
-        s->info.nwide = s->nwnodes; s->info.wide_levels = s->wide_levels;
-        int hb[6];
         DRB_CUDA(cudaMemcpyAsync(hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
-        DRB_CUDA(cudaEventRecord(e2, st));
-        DRB_CUDA(cudaStreamSynchronize(st));
-        DRB_CUDA(cudaGetLastError());
-        for (int a = 0; a < 3; ++a) { s->info.bounds_min[a] = ordered_to_float(hb[a]); s->info.bounds_max[a] = ordered_to_float(hb[3 + a]); }
-    } else {
-        DRB_CUDA(cudaEventRecord(e2, st));
-        DRB_CUDA(cudaStreamSynchronize(st));
+        DRB_CUDA(cudaMemcpyAsync(&ctl, d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, st));
     }
-    s->info.max_depth = height;
+    DRB_CUDA(cudaEventRecord(ev.e[2], st));
+    DRB_CUDA(cudaStreamSynchronize(st));                     // the one synchronisation of the build
+    DRB_CUDA(cudaGetLastError());
+    if (nprims > 0) {
+        if (ctl.packed != nprims) { drb_set_error("the device packed %d renderable objects, the host scene counted %d", ctl.packed, nprims); return DRB_ERR_ARG; }
+        if (ctl.error == 1) { drb_set_error("hierarchy rebuild made no progress (%d clusters left after %d rounds)", ctl.ploc_n, ctl.rounds); return DRB_ERR_CUDA; }
+        if (ctl.error == 2) { drb_set_error("wide collapse overran (%d nodes, level %d)", ctl.nwide, ctl.wide_levels); return DRB_ERR_CUDA; }
+        for (int a = 0; a < 3; ++a) { s->info.bounds_min[a] = ordered_to_float(hb[a]); s->info.bounds_max[a] = ordered_to_float(hb[3 + a]); }
+        if (nprims > 1) { s->nwnodes = ctl.nwide; s->wide_levels = ctl.wide_levels; s->stack_levels = ctl.stack_need + 2; s->info.max_depth = ctl.height; }
+        else { s->nwnodes = 1; s->wide_levels = 1; s->stack_levels = 3; s->info.max_depth = 1; }
+        s->info.rebuild_iterations = ctl.rounds;
+        s->info.nwide = s->nwnodes; s->info.wide_levels = s->wide_levels; s->info.stack_levels = s->stack_levels;
+    }
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1); s->info.upload_ms = ms;
-    cudaEventElapsedTime(&ms, e1, e2); s->info.build_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    if (height > kMaxTreeHeight) {
-        drb_set_error("LBVH height %d exceeds the traversal stack (%d)", height, kMaxTreeHeight);
+    cudaEventElapsedTime(&ms, ev.e[0], ev.e[1]); s->info.upload_ms = ms;
+    cudaEventElapsedTime(&ms, ev.e[1], ev.e[2]); s->info.build_ms = ms;
+    // the traversal stack lives in shared memory, one column per lane: what limits a scene is that, not the tree height
+    if ((size_t)s->stack_levels * 128 * sizeof(int) > (size_t)200 * 1024) {
+        drb_set_error("traversal stack of %d levels does not fit in shared memory", s->stack_levels);
         return DRB_ERR_UNSUPPORTED;
     }
     return DRB_OK;
@@ -827,9 +974,14 @@ void drb_scene_free(drb_scene* s)
     delete s;
 }
 
-int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out) { return drb_scene_create_ex(hs, device, 0u, out); }
+int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out) { return drb_scene_create_from_device(hs, device, 0u, nullptr, nullptr, out); }
 
 int drb_scene_create_ex(const drb_host_scene* hs, int device, uint32_t build_flags, drb_scene** out)
+{
+    return drb_scene_create_from_device(hs, device, build_flags, nullptr, nullptr, out);
+}
+
+int drb_scene_create_from_device(const drb_host_scene* hs, int device, uint32_t build_flags, const void* objects_dev, void* stream, drb_scene** out)
 {
     if (!hs || !out) { drb_set_error("drb_scene_create: null argument"); return DRB_ERR_ARG; }
     *out = nullptr;
@@ -848,13 +1000,23 @@ int drb_scene_create_ex(const drb_host_scene* hs, int device, uint32_t build_fla
     cudaError_t ce = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { drb_set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); delete s; return DRB_ERR_CUDA; }
     if (int prc = retain_pool(device)) { cudaStreamDestroy(s->stream); delete s; return prc; }
-    // page-lock the object lines once per host scene so the upload runs at PCIe speed (and again for free next frame)
-    if (!hs->objects.empty() && !hs->pinned) {
+    int rc = DRB_OK;
+    if (objects_dev) {
+        // the build runs on the scene's stream: order it after whatever produced the array
+        cudaEvent_t ready = nullptr;
+        if (cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ready, (cudaStream_t)stream) != cudaSuccess ||
+            cudaStreamWaitEvent(s->stream, ready, 0) != cudaSuccess) {
+            drb_set_error("cannot order the build after the caller's stream: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = DRB_ERR_CUDA;
+        }
+        if (ready) cudaEventDestroy(ready);
+    } else if (!hs->objects.empty() && !hs->pinned) {
+        // page-lock the object lines once per host scene so the upload runs at PCIe speed (and again for free next frame)
         if (cudaHostRegister((void*)hs->objects.data(), hs->objects.size() * sizeof(drb_object), cudaHostRegisterPortable) == cudaSuccess) hs->pinned = true;
         else cudaGetLastError();
     }
-    int rc = upload_textures(s, hs);
-    if (rc == DRB_OK) rc = build_tree(s, hs);
+    if (rc == DRB_OK) rc = upload_textures(s, hs);
+    if (rc == DRB_OK) rc = build_tree(s, hs, (const drb_object*)objects_dev);
     if (rc != DRB_OK) { std::string keep = drb_last_error(); drb_scene_free(s); drb_set_error("%s", keep.c_str()); return rc; }
     if (s->settings.backtex >= s->ntextures) s->settings.backtex = -1;
     *out = s;
@@ -891,6 +1053,7 @@ int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* 
                    float* node_min, float* node_max)
 {
     if (!s) { drb_set_error("drb_scene_lbvh: null scene"); return DRB_ERR_ARG; }
+    if (!(s->build_flags & DRB_BUILD_KEEP_DEBUG)) { drb_set_error("drb_scene_lbvh: the scene was not created with DRB_BUILD_KEEP_DEBUG"); return DRB_ERR_UNSUPPORTED; }
     DRB_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)s->nprims, ni = n > 1 ? n - 1 : 0;
     if (keys && n) DRB_CUDA(cudaMemcpy(keys, s->dbg.keys, n * 8, cudaMemcpyDeviceToHost));
@@ -931,6 +1094,7 @@ int drb_scene_wide(const drb_scene* s, int32_t* child, uint32_t* boxes)
 int drb_scene_tree(const drb_scene* s, int32_t* left, int32_t* right, float* node_min, float* node_max)
 {
     if (!s) { drb_set_error("drb_scene_tree: null scene"); return DRB_ERR_ARG; }
+    if (!(s->build_flags & DRB_BUILD_KEEP_DEBUG)) { drb_set_error("drb_scene_tree: the scene was not created with DRB_BUILD_KEEP_DEBUG"); return DRB_ERR_UNSUPPORTED; }
     DRB_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)s->nprims, ni = n > 1 ? n - 1 : 0;
     if (left && ni) DRB_CUDA(cudaMemcpy(left, s->tree.left, ni * 4, cudaMemcpyDeviceToHost));

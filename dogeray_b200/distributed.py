@@ -60,6 +60,10 @@ def render_sharded(render_fn: Callable[[int, int], "object"], spp: int, rank: in
                    reduce_dst: Optional[int] = 0):
     """Trace this rank's share with render_fn(base, count) -> tensor of radiance SUMS, then reduce.
 
+    A rank's share may be empty (spp < world): render_fn is then called with count == 0 and must return zeros --
+    Scene.render_device(sample_count=0) does exactly that (an integer sample_count is taken literally,
+    DRB_FLAG_EXACT_SAMPLES; only sample_count=None means "the settings' spp").
+
     Returns (tensor, count): on `reduce_dst` (or on every rank when reduce_dst is None -> all-reduce)
     the tensor holds the sum over all spp samples; elsewhere its contents are unspecified.
     """
@@ -84,7 +88,8 @@ def render_progressive(render_fn: Callable[[int, int], "object"], spp: int, chun
     (all ranks if None) and added to the running total.  Yields (total, samples_done) after every chunk: on the
     destination rank `total` is the sum over all samples so far (divide by samples_done for the mean image); other
     ranks get their local partial and should only use the count.  One reduce of W*H*3 floats per chunk is the only
-    traffic between ranks.
+    traffic between ranks.  With chunk < world some ranks have an empty share of a chunk: render_fn(base, 0) must
+    return zeros (see render_sharded).
     """
     import torch
     import torch.distributed as dist

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DRB_ABI_VERSION 1
+#define DRB_ABI_VERSION 2
 
 typedef enum drb_status {
     DRB_OK = 0,
@@ -107,6 +107,8 @@ const drb_object* drb_host_scene_objects(const drb_host_scene* hs);
 int drb_host_scene_settings(const drb_host_scene* hs, drb_settings* out);
 int drb_host_scene_num_textures(const drb_host_scene* hs);
 const char* drb_host_scene_texture_path(const drb_host_scene* hs, int i);
+/* objects that become primitives of the tree (type 0 / 2 with enough columns); counted on first call, then remembered */
+int64_t drb_host_scene_num_renderable(const drb_host_scene* hs);
 /* lines skipped while parsing (unsupported type, junk line); see drb_last_error() for the first */
 int64_t drb_host_scene_num_skipped(const drb_host_scene* hs);
 /* Write a scene in the exporter's format (plugin/rtsexport.py:207, 312-314). */
@@ -124,7 +126,17 @@ int drb_scene_create(const drb_host_scene* hs, int device, drb_scene** out);
  * build); by default the hierarchy is rebuilt over the same Morton order by SAH-guided agglomerative
  * clustering, which traverses ~1.4x faster. */
 #define DRB_BUILD_LBVH_ONLY 1u
+/* DRB_BUILD_KEEP_DEBUG keeps the integer outputs of the build (keys, order, both binary hierarchies: ~100 B per
+ * primitive) resident for drb_scene_lbvh / drb_scene_tree; without it they are scratch and those getters fail. */
+#define DRB_BUILD_KEEP_DEBUG 2u
 int drb_scene_create_ex(const drb_host_scene* hs, int device, uint32_t build_flags, drb_scene** out);
+/* Same, with the object lines ALREADY in device memory: `objects_dev` points at drb_host_scene_num_objects(hs) records
+ * of drb_object on `device`, in file order (e.g. each rank uploaded 1/N of them and one all-gather over NVLink
+ * completed the array -- the per-frame upload of CudaStarter, kernel.cu:2604-2629, paid once per node instead of once per
+ * GPU).  `stream` (a cudaStream_t, may be NULL) is the stream the array was produced on: the build waits for it.  `hs`
+ * supplies settings, textures and counts; the array is only read during the call. */
+int drb_scene_create_from_device(const drb_host_scene* hs, int device, uint32_t build_flags, const void* objects_dev, void* stream,
+                                 drb_scene** out);
 /* convenience: drb_host_scene_load + drb_scene_create */
 int drb_scene_load(const char* rts_path, const char* tex_dir, int device, drb_scene** out);
 void drb_scene_free(drb_scene* s);
@@ -140,11 +152,12 @@ typedef struct drb_build_info {
     int32_t rebuild_iterations; /* clustering rounds of the SAH-guided rebuild (0 with DRB_BUILD_LBVH_ONLY) */
     int64_t nwide;              /* four-wide traversal nodes */
     int32_t wide_levels;        /* height of the four-wide tree */
+    int32_t stack_levels;       /* traversal stack entries per lane (exact bound computed by the collapse) */
 } drb_build_info;
 int drb_scene_build_info(const drb_scene* s, drb_build_info* out);
 
-/* Integer outputs of the GPU LBVH build, for the bit-exact check against a host build.
- * Any pointer may be NULL.  keys: n 64-bit sort keys in sorted order; order: n prim slots in
+/* Integer outputs of the GPU LBVH build, for the bit-exact check against a host build (scenes created with
+ * DRB_BUILD_KEEP_DEBUG; DRB_ERR_UNSUPPORTED otherwise).  Any pointer may be NULL.  keys: n 64-bit sort keys in sorted order; order: n prim slots in
  * sorted order; parent/left/right: n-1 internal nodes, children >= 0 are internal nodes,
  * children < 0 are leaves encoded as ~sorted_position; node_min/node_max: 3 floats per
  * internal node. */
@@ -152,7 +165,7 @@ int drb_scene_lbvh(const drb_scene* s, uint64_t* keys, int32_t* order, int32_t* 
                    float* node_min, float* node_max);
 
 /* The hierarchy the traversal nodes were emitted from, root = node 0, same child encoding as
- * drb_scene_lbvh; equals the Karras tree with DRB_BUILD_LBVH_ONLY.  For the bit-exact host check. */
+ * drb_scene_lbvh; equals the Karras tree with DRB_BUILD_LBVH_ONLY.  For the bit-exact host check (DRB_BUILD_KEEP_DEBUG). */
 int drb_scene_tree(const drb_scene* s, int32_t* left, int32_t* right, float* node_min, float* node_max);
 
 /* The four-wide traversal nodes (collapsed from drb_scene_tree's hierarchy): child[4*i + k] is child k of node i
@@ -164,7 +177,7 @@ int drb_scene_wide(const drb_scene* s, int32_t* child, uint32_t* boxes);
 typedef struct drb_opts {
     uint64_t seed;              /* Philox key */
     uint32_t sample_base;       /* first sample index of this call */
-    uint32_t sample_count;      /* samples per pixel to trace in this call; 0 -> settings->spp */
+    uint32_t sample_count;      /* samples per pixel to trace in this call; 0 -> settings->spp, unless DRB_FLAG_EXACT_SAMPLES */
     uint32_t batch_paths;       /* paths in flight per wavefront batch; 0 -> 128 M (15 GB of queues), at most 1/4 of device memory */
     uint32_t flags;             /* DRB_FLAG_* */
     void* stream;               /* cudaStream_t to launch on; NULL -> the scene's own stream */
@@ -172,6 +185,9 @@ typedef struct drb_opts {
     uint32_t tile_count;        /* pixels of other tiles are left untouched in accum.  0 or 1 -> the whole image      */
 } drb_opts;
 #define DRB_FLAG_ACCUMULATE 1u  /* add into accum instead of overwriting it */
+/* sample_count is taken literally: 0 traces nothing (accum is zeroed, or left alone with DRB_FLAG_ACCUMULATE).  A rank
+ * whose share of a sharded frame is empty (spp < ranks, distributed.shard_samples) passes its count with this flag. */
+#define DRB_FLAG_EXACT_SAMPLES 2u
 
 typedef struct drb_stats {
     uint64_t paths;             /* camera paths traced */

@@ -677,6 +677,41 @@ void orc_hit_brute(const orc_scene* s, const float* o3, const float* d3, int n, 
     }
 }
 
+/* Closest hit by definition over TRIANGLE ARRAYS (no scene file, no tree): hit_tri (kernel.cu:277-313) against every
+ * triangle, acceptance as singlehit / hit (:449, :488: 0 < t < 10000, strictly closer wins, so the lowest index keeps
+ * an exact tie).  For scenes too large to push through the text format in a test (10 M triangles): rays are split
+ * over `threads` host threads.  v0/v1/v2: n*3 floats; t: nrays (or -1), id: nrays (or -1). */
+typedef struct { const float *v0, *v1, *v2, *o3, *d3; int n, r0, r1; float* t; int* id; } brute_job;
+static void* brute_worker(void* arg)
+{
+    brute_job* j = (brute_job*)arg;
+    for (int i = j->r0; i < j->r1; i++) {
+        v3 o = V(j->o3[3 * i], j->o3[3 * i + 1], j->o3[3 * i + 2]), d = V(j->d3[3 * i], j->d3[3 * i + 1], j->d3[3 * i + 2]);
+        float best = 10000; int g = -1;
+        for (int k = 0; k < j->n; k++) {
+            const float *a = j->v0 + 3 * (size_t)k, *b = j->v1 + 3 * (size_t)k, *c = j->v2 + 3 * (size_t)k;
+            float tt = hit_tri(o, d, V(a[0], a[1], a[2]), V(b[0], b[1], b[2]), V(c[0], c[1], c[2]));
+            if (tt > -0.0 && tt < best) { best = tt; g = k; }
+        }
+        j->t[i] = g >= 0 ? best : -1; j->id[i] = g;
+    }
+    return NULL;
+}
+void orc_brute_tris(const float* v0, const float* v1, const float* v2, int n, const float* o3, const float* d3, int nrays, float* t, int* id, int threads)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    if (threads > nrays) threads = nrays > 0 ? nrays : 1;
+    pthread_t th[256]; brute_job jobs[256];
+    for (int k = 0; k < threads; k++) {
+        brute_job j = { v0, v1, v2, o3, d3, n, (int)((long long)nrays * k / threads), (int)((long long)nrays * (k + 1) / threads), t, id };
+        jobs[k] = j;
+        if (k > 0) pthread_create(&th[k], NULL, brute_worker, &jobs[k]);
+    }
+    brute_worker(&jobs[0]);
+    for (int k = 1; k < threads; k++) pthread_join(th[k], NULL);
+}
+
 /* one frame; out_f/out_i indexed (x*H + y)*3 like outputr; returns rays traced */
 uint64_t orc_frame(orc_scene* s, float* out_f, int* out_i, int divisor, unsigned sample_base, int threads)
 {

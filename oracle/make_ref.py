@@ -77,6 +77,27 @@ def build_gpu(ref_root):
     return out
 
 
+def build_gpu_counting(ref_root):
+    """the same build with a ray counter in front of raycolor's hit() call (kernel.cu:800).  The edited stream goes to a
+    temporary file outside the repo, which is gone when the compile is; only the .so lands in oracle/_ref."""
+    import tempfile
+    src = os.path.join(ref_root, "raygpu", "kernel.cu")
+    out = os.path.join(OUT, "libdogeray_ref_gpu_count.so")
+    with tempfile.TemporaryDirectory(prefix="drb_refcount_") as td:
+        edited = os.path.join(td, "kernel_counted.cu")
+        run(["bash", "-o", "pipefail", "-c", "sed '%s' '%s' > '%s'" % (COUNT_SED.replace("orc_rays++;", "refgpu_count_ray();"), src, edited)])
+        with open(edited) as f:
+            if "refgpu_count_ray();" not in f.read():
+                raise RuntimeError("the ray-counter edit did not apply (kernel.cu:800 changed?)")
+        run([
+            "nvcc", "-std=c++17", "-O3", "-arch=sm_100", "-w", "-Xcompiler", "-fPIC", "-shared",
+            "-I" + os.path.join(HERE, "stubs"), "-D_USE_MATH_DEFINES", "-Dmain=ref_main", "-DREF_COUNT_RAYS",
+            '-DREF_KERNEL_CU="%s"' % edited,
+            os.path.join(HERE, "ref_gpu_driver.cu"), "-o", out,
+        ])
+    return out
+
+
 def stage_samples(ref_root):
     src = os.path.join(ref_root, "samples")
     dst = os.path.join(OUT, "samples")
@@ -108,6 +129,7 @@ def main(argv=None):
     build_host(args.reference)
     if not args.no_gpu:
         build_gpu(args.reference)
+        build_gpu_counting(args.reference)
     n = stage_samples(args.reference)
     print("staged %d sample files into %s" % (n, os.path.join(OUT, "samples")))
     return 0

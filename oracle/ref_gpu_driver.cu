@@ -15,6 +15,19 @@
  */
 #include <unistd.h>
 #include <limits.h>
+#include <cuda_runtime.h>
+#ifdef REF_COUNT_RAYS
+/* The ray-counting variant (libdogeray_ref_gpu_count.so): make_ref.py pipes kernel.cu through sed, which puts a call
+ * to refgpu_count_ray() in front of the single hit() call of raycolor (kernel.cu:800), into a temporary file outside
+ * the repo.  It exists to let the reference count ITS OWN rays; it is never the build that is timed. */
+__device__ unsigned long long refgpu_ray_counter;
+__device__ __forceinline__ void refgpu_count_ray()
+{
+    const unsigned m = __activemask();
+    const unsigned lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31u;
+    if (lane == (unsigned)(__ffs(m) - 1)) atomicAdd(&refgpu_ray_counter, (unsigned long long)__popc(m));
+}
+#endif
 #include REF_KERNEL_CU
 
 static singleobject* g_objs = nullptr;
@@ -115,6 +128,21 @@ void refgpu_set_settings(const float* in)
 }
 
 int refgpu_num_objects() { return nanum[0] - 1; }
+
+/* rays the reference's own raycolor traced since the last reset (counting variant only; -1 otherwise) */
+long long refgpu_rays(int reset)
+{
+#ifdef REF_COUNT_RAYS
+    unsigned long long v = 0, zero = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&v, refgpu_ray_counter, sizeof v);
+    if (reset) cudaMemcpyToSymbol(refgpu_ray_counter, &zero, sizeof zero);
+    return (long long)v;
+#else
+    (void)reset;
+    return -1;
+#endif
+}
 
 /* one CudaStarter() call; out = W*H*3 ints indexed x*H+y; returns the cudaError_t it returned */
 int refgpu_frame(int* out, int divisor, double* wall_ms)

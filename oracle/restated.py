@@ -29,6 +29,7 @@ def _load():
     L.orc_set_seed.argtypes = [C.c_void_p, C.c_uint64]
     L.orc_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_hit_brute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_brute_tris.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int]
     L.orc_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int]; L.orc_frame.restype = C.c_uint64
     L.orc_primary_rays.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
     L.orc_philox_word.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]; L.orc_philox_word.restype = C.c_uint32
@@ -107,6 +108,17 @@ class Restated:
         o = np.empty((H, W, 3), np.float32); d = np.empty((H, W, 3), np.float32)
         self.L.orc_primary_rays(self.h, sample, o.ctypes.data, d.ctypes.data)
         return o, d
+
+
+def brute_tris(v0, v1, v2, origins, dirs, threads=0):
+    """Closest hit by definition over triangle arrays (n,3) x3: (ids, t), -1 = miss; lowest index keeps exact ties."""
+    L = _load()
+    v0 = np.ascontiguousarray(v0, np.float32); v1 = np.ascontiguousarray(v1, np.float32); v2 = np.ascontiguousarray(v2, np.float32)
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3); d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    t = np.empty(len(o), np.float32); ids = np.empty(len(o), np.int32)
+    L.orc_brute_tris(v0.ctypes.data, v1.ctypes.data, v2.ctypes.data, len(v0), o.ctypes.data, d.ctypes.data, len(o), t.ctypes.data, ids.ctypes.data,
+                     threads or (os.cpu_count() or 1))
+    return ids, t
 
 
 def philox_word(seed, x, y, sample, n):

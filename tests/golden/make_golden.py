@@ -11,6 +11,9 @@ Vectors (all small, committed):
   synth_materials.npz    dogeray_b200.synth.materials_scene at 24x12 per blob (every material class of the reference,
                          colour + roughness textures, checker, smooth normals, environment map; textures from
                          synth.write_test_textures), 96x56, 3 spp, depth 6, seed 13: ids / t / float frame
+  bmp_headers.json       the file + BITMAPV4 headers (first 122 bytes, hex) of every screenshot the reference ships in
+                         images/*.bmp (SDL_SaveBMP output, kernel.cu:2505-2513) with their sizes: the only golden
+                         artefacts the reference holds for the image writer
   philox_kat.json        Random123 known-answer vectors for Philox4x32-10 (published with the algorithm)
 """
 import json
@@ -27,6 +30,22 @@ from dogeray_b200 import synth  # noqa: E402
 from oracle import refhost, restated  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def bmp_headers(out):
+    import glob
+    import struct
+    rec = {}
+    for p in sorted(glob.glob("/root/reference/images/*.bmp")):
+        with open(p, "rb") as f:
+            b = f.read()
+        off = struct.unpack_from("<I", b, 10)[0]
+        w, h = struct.unpack_from("<ii", b, 18)
+        rec[os.path.basename(p)] = {"file_size": len(b), "width": w, "height": h, "pixel_offset": off, "header_hex": b[:off].hex(),
+                                    "alpha_values": sorted(set(b[off + 3::4]))}
+    with open(out, "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("wrote", out, len(rec), "headers")
 
 
 def golden_for(ref, rts, texdir, st, seed, out):
@@ -47,6 +66,9 @@ def golden_for(ref, rts, texdir, st, seed, out):
 
 
 def main():
+    bmp_headers(os.path.join(HERE, "bmp_headers.json"))
+    if "--bmp-only" in sys.argv:
+        return
     ref = refhost.RefHost()
     objs, st = synth.heightfield_scene(n=24, width=48, height=40, spp=3, max_depth=5)
     with tempfile.TemporaryDirectory() as td:

@@ -61,7 +61,7 @@ def render(base, count):
     s = st.replace(spp=max(count, 1))
     r.apply(s); r.set_seed(3)
     f, _, _ = r.frame(1, base, threads=1)                      # 255 * mean over `count` samples, (W,H,3)
-    return torch.from_numpy((f.astype(np.float64) * count / 255.0).astype(np.float32)) if count else torch.zeros(st.width, st.height, 3)
+    return torch.from_numpy((f.astype(np.float64) * count / 255.0).astype(np.float32))          # count == 0 (an empty share) -> zeros
 
 acc, count = render_sharded(render, st.spp, rank, world)
 if rank == 0:
@@ -80,6 +80,20 @@ assert snaps == [2, 4, 5], snaps
 if rank == 0:
     err = float(np.abs(last.numpy() / st.spp * 255.0 - full).max())
     print("PROGRESSIVE_MAXERR %g" % err)
+    assert err < 2e-3, err
+# fewer samples than ranks: rank 1's share of every 1-sample chunk is empty and must contribute nothing
+calls = []
+def render_logged(base, count):
+    calls.append((base, count))
+    return render(base, count)
+for total, done in render_progressive(render_logged, 3, 1, rank, world):
+    last1 = total
+assert calls == ([(0, 1), (1, 1), (2, 1)] if rank == 0 else [(1, 0), (2, 0), (3, 0)]), calls
+if rank == 0:
+    r.apply(st.replace(spp=3)); r.set_seed(3)
+    three, _, _ = r.frame(1, 0, threads=1)
+    err = float(np.abs(last1.numpy() / 3 * 255.0 - three).max())
+    print("EMPTY_SHARE_MAXERR %g" % err)
     assert err < 2e-3, err
 # tile sharding: each rank contributes only the pixels of its tiles; the reduced image IS the full frame, bit for bit
 from dogeray_b200.distributed import tile_owner_mask
@@ -105,4 +119,4 @@ def test_two_rank_gloo_sample_sharding(tmp_path):
            "--master-port", "29533", str(script), ROOT, str(tmp_path)]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "MAXERR" in p.stdout and "PROGRESSIVE_MAXERR" in p.stdout and "TILES_BIT_IDENTICAL" in p.stdout
+    assert "MAXERR" in p.stdout and "PROGRESSIVE_MAXERR" in p.stdout and "TILES_BIT_IDENTICAL" in p.stdout and "EMPTY_SHARE_MAXERR" in p.stdout

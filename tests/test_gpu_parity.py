@@ -226,6 +226,18 @@ def test_edge_scenes_empty_single_and_spheres():
     assert ids.tolist() == [1]
 
 
+def wide_stack_need(child):
+    """Exact bound of traversal pushes over a four-wide tree (the host side of k_wide_all's last pass): a visit pushes all
+    but one of a node's children, so need(node) = (children - 1) + max over internal children of need(child).  Children
+    have larger ids than their parent (breadth-first ids), so one backwards sweep does it."""
+    EMPTY = -2 ** 31
+    need = np.zeros(len(child), np.int64)
+    for i in range(len(child) - 1, -1, -1):
+        kids = [c for c in child[i] if c != EMPTY]
+        need[i] = max(len(kids) - 1, 0) + max([need[c] for c in kids if c >= 0], default=0)
+    return int(need[0])
+
+
 def test_gpu_lbvh_bit_exact_against_host_build():
     rng = np.random.default_rng(8)
     cases = []
@@ -244,7 +256,7 @@ def test_gpu_lbvh_bit_exact_against_host_build():
     if HAVE_REF:
         cases.append(drb.HostScene.load(sample("SPERSSSSS.rts")).objects())
     for objs in cases:
-        sc = drb.Scene.from_host(drb.HostScene.from_objects(objs))
+        sc = drb.Scene.from_host(drb.HostScene.from_objects(objs), build_flags=drb.BUILD_KEEP_DEBUG)
         tri = objs["type"] == 2
         v = np.stack([objs["pos"], objs["dim"], objs["rot"]], 1)
         bmin = np.where(tri[:, None], v.min(1), objs["pos"] - np.abs(objs["dim"][:, :1]))
@@ -269,10 +281,85 @@ def test_gpu_lbvh_bit_exact_against_host_build():
             dw = sc.wide()
             assert bi.nwide == len(wh["child"]) and bi.wide_levels == wh["levels"]
             assert np.array_equal(dw["child"], wh["child"]) and np.array_equal(dw["boxes"], wh["boxes"])
-            lb = drb.Scene.from_host(drb.HostScene.from_objects(objs), build_flags=drb.BUILD_LBVH_ONLY)
+            assert bi.stack_levels == wide_stack_need(wh["child"]) + 2 <= 3 * wh["levels"] + 2
+            # the default build keeps none of the debug arrays, and emits the same traversal nodes
+            plain = drb.Scene.from_host(drb.HostScene.from_objects(objs))
+            pw = plain.wide()
+            assert np.array_equal(pw["child"], wh["child"]) and np.array_equal(pw["boxes"], wh["boxes"])
+            assert plain.build_info.stack_levels == bi.stack_levels and plain.build_info.max_depth == bi.max_depth
+            with pytest.raises(drb.DogerayError):
+                plain.lbvh()
+            with pytest.raises(drb.DogerayError):
+                plain.tree()
+            lb = drb.Scene.from_host(drb.HostScene.from_objects(objs), build_flags=drb.BUILD_LBVH_ONLY | drb.BUILD_KEEP_DEBUG)
             assert lb.build_info.max_depth == host["height"] and lb.build_info.rebuild_iterations == 0
             lt = lb.tree()
             assert np.array_equal(lt["left"], host["left"]) and np.array_equal(lt["right"], host["right"])
+
+
+def test_scene_from_object_lines_already_on_the_device():
+    """drb_scene_create_from_device: the build reads an array some other stream produced (e.g. an all-gather of per-rank
+    partial uploads) and gives the scene the host upload gives"""
+    import torch
+    objs, st = synth.heightfield_scene(n=48, width=64, height=40, spp=2, max_depth=4)
+    objs = np.concatenate([objs, drb.make_objects(3)])                     # degenerate + a legacy type that stays out of the tree
+    objs["type"][-1] = 1
+    hs = drb.HostScene.from_objects(objs, st)
+    assert hs.num_renderable == len(objs) - 1
+    a = drb.Scene.from_host(hs)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        halves = [torch.from_numpy(objs[:1000].view(np.uint8)).cuda(non_blocking=True), torch.from_numpy(objs[1000:].view(np.uint8)).cuda(non_blocking=True)]
+        dev = torch.cat(halves)                                            # stands in for the all-gather
+        b = drb.Scene.from_device_objects(hs, dev.data_ptr(), stream=side.cuda_stream)
+    wa, wb = a.wide(), b.wide()
+    assert np.array_equal(wa["child"], wb["child"]) and np.array_equal(wa["boxes"], wb["boxes"])
+    fa, sa = a.render(st, seed=2); fb, sb = b.render(st, seed=2)
+    assert np.array_equal(fa, fb) and sa.rays == sb.rays
+    # a host scene whose count disagrees with the device array is refused, not overrun
+    wrong = objs.copy(); wrong["type"][:10] = 1
+    with pytest.raises(drb.DogerayError):
+        drb.Scene.from_device_objects(drb.HostScene.from_objects(wrong, st), dev.data_ptr(), stream=side.cuda_stream)
+
+
+def test_zero_samples_means_zero_samples():
+    """an integer sample_count is literal (DRB_FLAG_EXACT_SAMPLES): the empty share of a sharded frame traces nothing"""
+    objs, st = synth.heightfield_scene(n=12, width=40, height=24, spp=3, max_depth=4)
+    sc = drb.Scene.from_host(drb.HostScene.from_objects(objs, st))
+    full, sf = sc.render(st, seed=9)                                        # sample_count=None -> settings.spp
+    assert sf.paths == 40 * 24 * 3
+    none, sn = sc.render(st, seed=9, sample_count=0)
+    assert sn.paths == 0 and sn.rays == 0 and not none.any()
+    kept, _ = sc.render(st, seed=9, sample_count=0, accumulate_into=full.copy())
+    assert np.array_equal(kept, full)
+    # spp < ranks: the shares of 8 ranks, summed, are the 3-sample frame
+    from dogeray_b200.distributed import shard_samples
+    acc = np.zeros_like(full)
+    for r in range(8):
+        base, count = shard_samples(st.spp, r, 8)
+        part, _ = sc.render(st, seed=9, sample_base=base, sample_count=count)
+        acc += part
+    assert np.allclose(acc, full, rtol=0, atol=1e-5)
+
+
+def test_small_scene_far_from_the_origin():
+    """ray padding larger than the scene (origin ~10^5 scene sizes away): an empty child slot's inverted box then passes
+    the slab test; its link has the stack sentinel's bits and must be dropped, not end the traversal"""
+    rng = np.random.default_rng(5)
+    n = 7                                                                    # 7 leaves: the four-wide tree has empty slots
+    o = drb.make_objects(n)
+    c = (np.array([4000.0, -3000.0, 5000.0]) + rng.uniform(-0.004, 0.004, (n, 3))).astype(np.float32)
+    o["pos"] = c; o["dim"] = c + rng.uniform(-0.004, 0.004, (n, 3)).astype(np.float32); o["rot"] = c + rng.uniform(-0.004, 0.004, (n, 3)).astype(np.float32)
+    sc = drb.Scene.from_host(drb.HostScene.from_objects(o))
+    assert (sc.wide()["child"] == -2 ** 31).any()
+    m = 4096
+    ro = (np.array([4000.0, -3000.0, 5000.0]) + rng.normal(size=(m, 3)) * 3).astype(np.float32)
+    tgt = c[rng.integers(0, n, m)] + rng.uniform(-0.003, 0.003, (m, 3))
+    rd = ((tgt - ro) * 40).astype(np.float32)                                # long directions: |det| clears hit_tri's epsilon
+    ids, t = sc.trace_ids(ro, rd)
+    bid, bt = restated.brute_tris(o["pos"], o["dim"], o["rot"], ro, rd)
+    assert (bid >= 0).sum() > 50
+    assert_ids_match(ids, t, bid, bt)
 
 
 def test_tonemap_device_matches_host():

@@ -50,7 +50,7 @@ def test_every_sample_scene(maybe_ref, name):
     assert_frames_match(acc.transpose(1, 0, 2) * np.float32(255.0) * np.float32(0.5), f)
 
 
-def random_scene(rng, n, scale):
+def random_scene(rng, n, scale, spheres=True, duplicates=True):
     o = drb.make_objects(n)
     c = rng.uniform(-1, 1, (n, 3)) * scale
     o["pos"] = c
@@ -70,14 +70,14 @@ def random_scene(rng, n, scale):
     o["smooth"] = rng.integers(0, 2, n)
     o["checker"] = (rng.uniform(size=n) < 0.2).astype(np.int32)
     o["t1"], o["t2"], o["t3"] = rng.uniform(0, 3, (n, 2)), rng.uniform(0, 3, (n, 2)), rng.uniform(0, 3, (n, 2))
-    sph = rng.uniform(size=n) < 0.1                                   # some spheres
+    sph = (rng.uniform(size=n) < 0.1) & spheres                       # some spheres
     o["type"][sph] = 0
     o["dim"][sph, 0] = rng.uniform(0.05, 0.4, int(sph.sum())) * scale
     o["mat"][sph & (o["mat"] == 4)] = 3                               # glass spheres need an inside hit the reference does not have
     o["checker"][sph] = 0                                             # getnormal leaves texco uninitialised for spheres (kernel.cu:707-710): UB with the checker
     deg = rng.uniform(size=n) < 0.05                                  # zero-area triangles
     o["rot"][deg] = o["dim"][deg]
-    dup = rng.uniform(size=n) < 0.05                                  # exact duplicates (all keys tie, equal t)
+    dup = (rng.uniform(size=n) < 0.05) & duplicates                   # exact duplicates (all keys tie, equal t)
     src = rng.integers(0, n, n)
     for k in ("pos", "dim", "rot", "type"):
         o[k][dup] = o[k][src[dup]]
@@ -90,7 +90,9 @@ def test_random_scenes(tmp_path, maybe_ref, seed):
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.choice([3, 17, 64, 300, 1500]))
     scale = float(rng.choice([0.5, 3.0, 40.0]))
-    objs = random_scene(rng, n, scale)
+    # seeds 0-5: triangles only, no exact duplicates -> the strict bar; 6-8: + spheres; 9-11: + duplicated objects
+    spheres, duplicates = seed >= 6, seed >= 9
+    objs = random_scene(rng, n, scale, spheres, duplicates)
     st = drb.default_settings().replace(cam=(0.3 * scale, -0.2 * scale, 2.8 * scale), look=(0, 0, 0), width=72, height=48, spp=2, max_depth=6,
                                         focus=3.0, aperture=float(rng.choice([0.0, 0.01, 0.2])), fov=int(rng.choice([30, 45, 70])))
     p = str(tmp_path / "r.rts")
@@ -115,8 +117,24 @@ def test_random_scenes(tmp_path, maybe_ref, seed):
     ours = acc.transpose(1, 0, 2) * np.float32(255.0) * np.float32(0.5)
     identical = float(np.mean(np.all(ours == f, axis=-1)))
     rmse = float(np.sqrt(np.mean(((ours - f) / 255.0) ** 2)))
-    # spheres: hit_sphere's powf(len, 2) is x*x here (an ulp apart now and then), and exact-t ties on duplicated objects
-    # may pick the twin with another material -- so not every pixel is bit-identical, but nearly all are
-    assert stats.rays == rays
-    assert identical >= 0.97 and rmse < 0.02, (identical, rmse)
     assert np.isfinite(acc).all()
+    if not spheres:
+        # nothing tree-dependent, nothing library-dependent: the stated tolerance and the bit-identity bar
+        assert stats.rays == rays
+        assert identical >= 0.999 and rmse <= 1e-3, (identical, rmse)
+    elif not duplicates:
+        # hit_sphere squares lengths with powf(len, 2) (kernel.cu:320, 324); the device squares with one multiply, which is
+        # the correctly rounded value glibc's powf misses by an ulp now and then -- a path may then take another branch
+        # (at 2 spp one such path in a 72x48 image is already 5e-3 of RMSE).  Nearly every pixel is still bit-identical,
+        # and the tolerance north_star states for CONVERGED radiance holds with room to spare at 64 spp.
+        assert abs(stats.rays - rays) <= 0.002 * rays and identical >= 0.99, (stats.rays, rays, identical)
+        st64 = st.replace(spp=64)
+        orc.apply(st64, seed)
+        f64, _, _ = orc.frame()
+        acc64, _ = sc.render(st64, seed=seed)
+        rmse64 = float(np.sqrt(np.mean(((acc64.transpose(1, 0, 2) * np.float32(255.0) * np.float32(1.0 / 64) - f64) / 255.0) ** 2)))
+        assert rmse64 <= 1e-3, rmse64
+    else:
+        # exact-t ties on duplicated objects keep the first one VISITED, which depends on the tree (the reference's median
+        # split vs the LBVH): the twin may carry another material.  ids were checked above under the tie rule.
+        assert identical >= 0.97 and rmse < 0.02, (identical, rmse)

@@ -233,6 +233,43 @@ def test_bmp_layout_is_sdl_savebmp_v4(tmp_path):
     assert (px[..., 3] == 255).all()
 
 
+def test_bmp_header_equals_the_reference_screenshots_byte_for_byte(tmp_path):
+    """tests/golden/bmp_headers.json holds the first 122 bytes of every images/*.bmp the reference ships (SDL_SaveBMP,
+    kernel.cu:2505-2513): a file of the same size must start with exactly those bytes, and alpha is 255 throughout"""
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "bmp_headers.json")) as f:
+        golden = json.load(f)
+    assert "bolter2.blend.rts.bmp" in golden and len(golden) >= 13
+    done = set()
+    for name, g in golden.items():
+        assert g["pixel_offset"] == 122 and g["alpha_values"] == [255]
+        key = (g["width"], g["height"])
+        if key in done:
+            continue
+        done.add(key)
+        img = np.zeros((g["height"], g["width"], 3), np.uint8)
+        img[0, 0] = (1, 2, 3)
+        p = str(tmp_path / "o.bmp")
+        drb.write_bmp(p, img)
+        b = open(p, "rb").read()
+        assert len(b) == g["file_size"], name
+        assert b[:122].hex() == g["header_hex"], name
+    assert (1280, 720) in done and len(done) >= 3
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/images"), reason="the reference's screenshots are not on this machine")
+def test_bmp_writer_reproduces_a_reference_screenshot_file(tmp_path):
+    """decode images/bolter2.blend.rts.bmp to top-down RGB and write it back: the file must come out byte-identical"""
+    ref = open("/root/reference/images/bolter2.blend.rts.bmp", "rb").read()
+    w, h = struct.unpack_from("<ii", ref, 18)
+    px = np.frombuffer(ref[122:], np.uint8).reshape(h, w, 4)[::-1]            # bottom-up rows, B G R A
+    rgb = np.ascontiguousarray(px[..., [2, 1, 0]])
+    p = str(tmp_path / "again.bmp")
+    drb.write_bmp(p, rgb)
+    assert open(p, "rb").read() == ref
+
+
 def test_ppm_writer_and_tonemap(tmp_path):
     acc = np.array([[[0.0, 0.5, 1.0], [2.0, -1.0, float("nan")]]], np.float32) * 4        # sum over 4 samples
     out = drb.tonemap(acc, 4)

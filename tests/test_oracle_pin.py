@@ -102,6 +102,26 @@ def test_restatement_against_golden_cube():
     _check_golden(g, restated.Restated(sample("cube.rts")))
 
 
+def test_brute_force_over_arrays_equals_the_scene_brute_force(tmp_path):
+    """orc_brute_tris (the 10 M-triangle check's definition of a closest hit) against orc_hit_brute and the tree walk"""
+    objs, st = synth.heightfield_scene(n=20, width=32, height=24, spp=1, max_depth=2)
+    p = str(tmp_path / "hf.rts")
+    drb.write_rts(p, st, objs)
+    objs = drb.HostScene.load(p).objects()                               # the floats the text holds
+    r = restated.Restated(p)
+    r.apply(st); r.set_seed(1)
+    o, d = r.primary_rays(0)
+    rng = np.random.default_rng(2)
+    o2 = rng.uniform(-5, 5, (500, 3)).astype(np.float32); d2 = rng.normal(size=(500, 3)).astype(np.float32)
+    allo = np.concatenate([o.reshape(-1, 3), o2]); alld = np.concatenate([d.reshape(-1, 3), d2])
+    a_id, a_t = restated.brute_tris(objs["pos"], objs["dim"], objs["rot"], allo, alld, threads=3)
+    b_id, b_t = r.hit_brute(allo, alld)
+    c_id, c_t = r.hit(allo, alld)
+    assert (a_id >= 0).sum() > 300
+    assert np.array_equal(a_id, b_id) and np.array_equal(a_t[a_id >= 0], b_t[a_id >= 0])
+    assert np.array_equal(a_id, c_id) and np.array_equal(a_t[a_id >= 0], c_t[a_id >= 0])
+
+
 def test_host_lbvh_is_a_valid_tree():
     rng = np.random.default_rng(4)
     for n in (1, 2, 3, 17, 1000):
