@@ -26,7 +26,7 @@ def test_header_symbols_exported():
 
 
 def test_abi_version_and_struct_sizes():
-    assert drb._lib.drb_abi_version() == 1
+    assert drb._lib.drb_abi_version() == 2
     assert ctypes.sizeof(drb.Settings) == 60
     assert drb.OBJECT_DTYPE.itemsize == 156
     assert ctypes.sizeof(drb.Opts) == 40
@@ -93,7 +93,7 @@ def _build_c_consumer(tmp_path):
 def test_header_is_plain_c_and_struct_sizes_agree(tmp_path):
     r = _build_c_consumer(tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "sizes settings=%d object=%d opts=%d stats=%d build_info=%d abi=1" % (
+    assert "sizes settings=%d object=%d opts=%d stats=%d build_info=%d abi=2" % (
         ctypes.sizeof(drb.Settings), drb.OBJECT_DTYPE.itemsize, ctypes.sizeof(drb.Opts), ctypes.sizeof(drb.Stats), ctypes.sizeof(drb.BuildInfo)) in r.stdout
     assert "parsed objects=2 width=16 height=8" in r.stdout
     if drb.device_count() == 0:
