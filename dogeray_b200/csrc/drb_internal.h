@@ -26,7 +26,10 @@ struct drb_host_scene {
     std::string first_warning;
     mutable bool pinned = false;          // objects[] page-locked by the first drb_scene_create (scene.cu)
     mutable int64_t renderable = -1;      // objects that go into the tree, counted on first use (drb_host_scene_num_renderable)
+    mutable std::vector<char> tex_used;   // per texture: some object or the settings line names it (same pass as `renderable`)
 };
+// one parallel pass over the objects that fills `renderable` and `tex_used` (idempotent; not thread-safe per scene)
+void drb_host_scene_summarise(const drb_host_scene* hs);
 
 // the rule for "this object line becomes a primitive": SURVEY.md App. B.9 (types other than 0 / 2 are undefined
 // behaviour in the reference) and junk lines that stop before the geometry columns; ncols == 0 = made in memory

@@ -72,6 +72,7 @@ struct FrameParams {
 
 struct DevScene {
     float qlo[3], qscale[3];            // quantisation grid of the node boxes (drb_quant_grid)
+    float pad_cap;                      // 0.49 x the largest grid extent: upper limit of the per-ray slab padding
     const WideNode* wnodes;
     const Prim* prims;
     const ShadeRec* recs;
@@ -279,7 +280,11 @@ __global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(D
                         const float ix = safe_inv(d.x), iy = safe_inv(d.y), iz = safe_inv(d.z);
                         // per-ray slab padding: on top of the quantisation margin the ray sees every box grown by a few
                         // ulps of the distances involved, so a hit the triangle test accepts by rounding is never culled
-                        const float pad = (fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + scene_scale) * 1.9073486e-6f;
+                        // An empty child slot (min 65535 > max 0) fails the test as long as twice the padding stays below the
+                        // grid's extent on ONE axis, so the padding is capped just under half the largest extent.  The cap only
+                        // binds for origins ~10^5 scene sizes away, where it still leaves tens of ulps of margin; without it such
+                        // a ray would follow empty links (they carry the stack sentinel's bits) and overrun the stack bound.
+                        const float pad = fminf((fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) + scene_scale) * 1.9073486e-6f, sc.pad_cap);
                         // plane coordinate = qlo + q * qscale; t = (coordinate -/+ pad - o) * inv, folded into one FMA on
                         // the float 2^23 + q: t = (2^23 + q) * s + (c - 2^23 * s).  The near plane is the min plane for a
                         // positive direction component and the max plane for a negative one.
@@ -346,10 +351,6 @@ __global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(D
         }
         // a lane that arrives at a leaf stashes it and keeps descending
         if (node < 0 && node != kSentinel && leaf == 0) { leaf = node; node = DRB_POP(); }
-        // an empty child slot carries the same bits as the stack-bottom sentinel; its inverted box cannot pass the slab
-        // test unless the ray's padding exceeds the whole scene (origin ~10^5 scene sizes away) -- then the stack is not
-        // empty and the link is simply dropped
-        while (node == kSentinel && sp != s_stack + threadIdx.x) node = DRB_POP();
         }
         // ---- postponed leaves -------------------------------------------------------------------------
         // The (long, divergent) primitive test runs for the whole warp at once when enough lanes hold a stashed
@@ -844,6 +845,7 @@ DevScene dev_scene(const drb_scene* s)
 {
     DevScene d;
     for (int a = 0; a < 3; ++a) drb_quant_grid(s->info.bounds_min[a], s->info.bounds_max[a], &d.qlo[a], &d.qscale[a]);
+    d.pad_cap = 0.49f * 65527.0f * std::max(d.qscale[0], std::max(d.qscale[1], d.qscale[2]));
     d.wnodes = s->wnodes; d.prims = s->prims; d.recs = s->recs; d.textures = s->textures;
     d.nprims = (int)s->nprims; d.ntextures = s->ntextures;
     return d;

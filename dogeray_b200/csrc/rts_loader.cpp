@@ -483,6 +483,40 @@ std::vector<std::string> drb_scan_textures(const char* tex_dir)
     return found;
 }
 
+void drb_host_scene_summarise(const drb_host_scene* hs)
+{
+    if (!hs || hs->renderable >= 0) return;
+    const size_t n = hs->objects.size(), ntex = hs->tex_paths.size();
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, n / 65536 + 1));
+    std::vector<int64_t> part((size_t)nt, 0);
+    std::vector<std::vector<char>> used((size_t)nt, std::vector<char>(ntex, 0));
+    auto count = [&](int t) {
+        const size_t lo = n * (size_t)t / (size_t)nt, hi = n * ((size_t)t + 1) / (size_t)nt;
+        int64_t c = 0;
+        std::vector<char>& u = used[(size_t)t];
+        for (size_t i = lo; i < hi; ++i) {
+            const drb_object& o = hs->objects[i];
+            c += drb_object_renderable(o) ? 1 : 0;
+            if (o.texnum >= 0 && (size_t)o.texnum < ntex) u[(size_t)o.texnum] = 1;
+            if (o.rtexnum >= 0 && (size_t)o.rtexnum < ntex) u[(size_t)o.rtexnum] = 1;
+        }
+        part[(size_t)t] = c;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(count, t);
+    count(0);
+    for (auto& th : pool) th.join();
+    int64_t total = 0;
+    hs->tex_used.assign(ntex, 0);
+    for (int t = 0; t < nt; ++t) {
+        total += part[(size_t)t];
+        for (size_t k = 0; k < ntex; ++k) hs->tex_used[k] |= used[(size_t)t][k];
+    }
+    if (hs->settings.backtex >= 0 && (size_t)hs->settings.backtex < ntex) hs->tex_used[(size_t)hs->settings.backtex] = 1;
+    hs->renderable = total;
+}
+
 extern "C" {
 
 const char* drb_last_error(void) { return g_last_error.c_str(); }
@@ -583,24 +617,8 @@ int drb_host_scene_create(const drb_settings* settings, const drb_object* object
 int64_t drb_host_scene_num_renderable(const drb_host_scene* hs)
 {
     if (!hs) return 0;
-    if (hs->renderable >= 0) return hs->renderable;
-    const size_t n = hs->objects.size();
-    const int nt = (int)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() : 1, n / 65536 + 1));
-    std::vector<int64_t> part((size_t)nt, 0);
-    auto count = [&](int t) {
-        const size_t lo = n * (size_t)t / (size_t)nt, hi = n * ((size_t)t + 1) / (size_t)nt;
-        int64_t c = 0;
-        for (size_t i = lo; i < hi; ++i) c += drb_object_renderable(hs->objects[i]) ? 1 : 0;
-        part[(size_t)t] = c;
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(count, t);
-    count(0);
-    for (auto& th : pool) th.join();
-    int64_t total = 0;
-    for (int64_t c : part) total += c;
-    hs->renderable = total;
-    return total;
+    drb_host_scene_summarise(hs);
+    return hs->renderable;
 }
 
 void drb_host_scene_free(drb_host_scene* hs) { if (hs) { drb_host_scene_unpin(hs); delete hs; } }

@@ -703,6 +703,22 @@ int retain_pool(int device)
     return DRB_OK;
 }
 
+// host-side stage times of a scene creation, printed with DOGERAY_B200_DEBUG set (how create's host overhead is found)
+struct StageClock {
+    bool on = getenv("DOGERAY_B200_DEBUG") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    std::string log;
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, " %s %.2f", what, std::chrono::duration<double, std::milli>(now - t).count());
+        log += buf; t = now;
+    }
+    void print(const char* who) { if (on) fprintf(stderr, "[dogeray_b200] %s host ms:%s\n", who, log.c_str()); }
+};
+
 struct EventTrio {
     cudaEvent_t e[3] = { nullptr, nullptr, nullptr };
     ~EventTrio() { for (auto x : e) if (x) cudaEventDestroy(x); }
@@ -735,10 +751,14 @@ int build_tree(drb_scene* s, const drb_host_scene* hs, const drb_object* objs_de
     const int64_t nobj = (int64_t)hs->objects.size();
     if (nobj >= (1ll << 31) - 8) { drb_set_error("too many objects (%lld)", (long long)nobj); return DRB_ERR_UNSUPPORTED; }
     cudaStream_t st = s->stream;
+    StageClock clk;
+    struct PrintOnExit { StageClock& c; ~PrintOnExit() { c.mark("scratch-free"); c.print("build_tree"); } };
     Scratch tmp(st);
+    PrintOnExit print_on_exit{ clk };                         // destroyed before tmp: "scratch-free" is then ~0; see drb_scene_create's own clock
     EventTrio ev;
     if (int rc = ev.create()) return rc;
     DRB_CUDA(cudaEventRecord(ev.e[0], st));
+    clk.mark("events");
 
     const bool keep = (s->build_flags & DRB_BUILD_KEEP_DEBUG) != 0;
     const bool lbvh_only = (s->build_flags & DRB_BUILD_LBVH_ONLY) != 0;
@@ -757,6 +777,7 @@ int build_tree(drb_scene* s, const drb_host_scene* hs, const drb_object* objs_de
     if (int rc = tmp.alloc(&d_ctl, 1)) return rc;
     DRB_CUDA(cudaMemsetAsync(d_ctl, 0, sizeof(BuildCtl), st));
     DRB_CUDA(cudaEventRecord(ev.e[1], st));
+    clk.mark("upload-enqueue");
 
     const int T = 256;
     s->nobjects = nobj;
@@ -888,7 +909,9 @@ int build_tree(drb_scene* s, const drb_host_scene* hs, const drb_object* objs_de
         DRB_CUDA(cudaMemcpyAsync(&ctl, d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, st));
     }
     DRB_CUDA(cudaEventRecord(ev.e[2], st));
+    clk.mark("build-enqueue");
     DRB_CUDA(cudaStreamSynchronize(st));                     // the one synchronisation of the build
+    clk.mark("sync");
     DRB_CUDA(cudaGetLastError());
     if (nprims > 0) {
         if (ctl.packed != nprims) { drb_set_error("the device packed %d renderable objects, the host scene counted %d", ctl.packed, nprims); return DRB_ERR_ARG; }
@@ -915,10 +938,9 @@ int upload_textures(drb_scene* s, const drb_host_scene* hs)
 {
     const int nt = (int)hs->tex_paths.size();
     s->ntextures = nt;
+    drb_host_scene_summarise(hs);                              // which textures the scene names: one pass per host scene, not per create
     std::vector<char> used((size_t)std::max(nt, 1), 0);
-    auto mark = [&](int k) { if (k >= 0 && k < nt) used[(size_t)k] = 1; };
-    mark(hs->settings.backtex);
-    for (const drb_object& o : hs->objects) { mark(o.texnum); mark(o.rtexnum); }
+    for (int k = 0; k < nt && k < (int)hs->tex_used.size(); ++k) used[(size_t)k] = hs->tex_used[(size_t)k];
     std::vector<DevTexture> table((size_t)std::max(nt, 1));
     for (int i = 0; i < nt; ++i) {
         table[(size_t)i] = DevTexture{ nullptr, 0, 0 };
@@ -993,6 +1015,7 @@ int drb_scene_create_from_device(const drb_host_scene* hs, int device, uint32_t 
     }
     if (device < 0 || device >= ndev) { drb_set_error("device %d out of range (0..%d)", device, ndev - 1); return DRB_ERR_ARG; }
     DRB_CUDA(cudaSetDevice(device));
+    StageClock clk;
     auto s = new drb_scene();
     s->device = device;
     s->build_flags = build_flags;
@@ -1015,8 +1038,12 @@ int drb_scene_create_from_device(const drb_host_scene* hs, int device, uint32_t 
         if (cudaHostRegister((void*)hs->objects.data(), hs->objects.size() * sizeof(drb_object), cudaHostRegisterPortable) == cudaSuccess) hs->pinned = true;
         else cudaGetLastError();
     }
+    clk.mark("stream+pool+pin");
     if (rc == DRB_OK) rc = upload_textures(s, hs);
+    clk.mark("textures");
     if (rc == DRB_OK) rc = build_tree(s, hs, (const drb_object*)objects_dev);
+    clk.mark("build_tree");
+    clk.print("drb_scene_create");
     if (rc != DRB_OK) { std::string keep = drb_last_error(); drb_scene_free(s); drb_set_error("%s", keep.c_str()); return rc; }
     if (s->settings.backtex >= s->ntextures) s->settings.backtex = -1;
     *out = s;
