@@ -110,6 +110,10 @@ DRB_D bool slot_to_pixel(const FrameParams& fp, uint32_t slot, int& x, int& y, u
 // order C++ leaves unspecified.  The oracle build (g++) evaluates it right to left, so the FIRST
 // draw of an attempt lands in the LAST component; the stream is consumed the same way here so that
 // paths stay aligned with the oracle draw for draw.  (Any order is the same distribution.)
+// The rejection test.  The reference rejects when pow(getLength(p), 2) >= 1 with getLength = sqrtf(dot(p, p))
+// (kernel.cu:200-203, 641); that is decided by d = dot(p, p) alone, without the square root: for d >= 1 the correctly
+// rounded root is >= 1 and so is its square; for d < 1 the root rounds to at most 1 - 2^-24 (sqrt(1 - 2^-24) lies below
+// the midpoint 1 - 2^-25), whose square, under powf's sub-ulp error as under a float multiply, stays below 1.
 DRB_D f3 random_in_unit_sphere(PathRng& rng)
 {
     for (;;) {
@@ -117,8 +121,7 @@ DRB_D f3 random_in_unit_sphere(PathRng& rng)
         rng.words3(wc, wb, wa);
         const float c = PathRng::to_uniform(wc), b = PathRng::to_uniform(wb), a = PathRng::to_uniform(wa);
         const f3 p = mk3(a * 2.0f - 1.0f, b * 2.0f - 1.0f, c * 2.0f - 1.0f);
-        const float l = length(p);
-        if (l * l >= 1.0f) continue;
+        if (dot(p, p) >= 1.0f) continue;                 // == the reference's pow(getLength(p), 2) >= 1 (see above)
         return p;
     }
 }
@@ -127,8 +130,7 @@ DRB_D f3 random_in_unit_disk(PathRng& rng)
     for (;;) {
         const float b = rng.uniform(), a = rng.uniform();
         const f3 p = mk3(a * 2.0f - 1.0f, b * 2.0f - 1.0f, 0.0f);
-        const float l = length(p);
-        if (l * l >= 1.0f) continue;
+        if (dot(p, p) >= 1.0f) continue;
         return p;
     }
 }

@@ -279,6 +279,7 @@ __global__ void k_refit(int n, const float4* __restrict__ lmin, const float4* __
 #define DRB_PLOC_RADIUS 16
 #endif
 constexpr int kPlocRadius = DRB_PLOC_RADIUS;
+constexpr int kPlocSoloClusters = 2048;     // from here on one block finishes the clustering (block barriers instead of grid barriers)
 
 __device__ __forceinline__ float union_half_area(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi)
 {
@@ -331,16 +332,26 @@ __global__ void __launch_bounds__(kBuildThreads) k_ploc_all(int n0, const float4
                                                             int32_t* left, int32_t* right, float4* node_min, float4* node_max, BuildCtl* ctl)
 {
     cg::grid_group grid = cg::this_grid();
-    const int nb = (int)gridDim.x, b = (int)blockIdx.x, t = (int)threadIdx.x;
+    const int b = (int)blockIdx.x, t = (int)threadIdx.x;
     int32_t* cid[2] = { cid0, cid1 }; float4* cmn[2] = { cmn0, cmn1 }; float4* cmx[2] = { cmx0, cmx1 };
-    for (int i = b * kBuildThreads + t; i < n0; i += nb * kBuildThreads) {
+    for (int i = b * kBuildThreads + t; i < n0; i += (int)gridDim.x * kBuildThreads) {
         cid0[i] = ~i;
         float4 lo = lmin[i]; lo.w = 0.f;
         cmn0[i] = lo; cmx0[i] = lmax[i];
     }
     grid.sync();
     int n = n0, node_base = 0, cur = 0, rounds = 0, err = 0;
+    // Once few clusters are left (most of the ~60 rounds), block 0 finishes alone: a block barrier costs a fraction of a
+    // grid barrier and the work no longer fills more than one block anyway.  The switch depends on n only, which every
+    // block knows, so the others leave after the grid barrier that ends their last common round.
+    bool solo = false;
+    int nb = (int)gridDim.x;
+    auto barrier = [&]() { if (solo) __syncthreads(); else grid.sync(); };
     while (n > 1) {
+        if (!solo && n <= kPlocSoloClusters) {
+            if (b != 0) break;
+            solo = true; nb = 1;
+        }
         const int chunk = max((n + nb - 1) / nb, kBuildThreads);
         const int c0 = min(n, b * chunk), c1 = min(n, c0 + chunk);
         const float4* cmin = cmn[cur]; const float4* cmax = cmx[cur];
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_ploc_all(int n0, const float4
             if (bj < 0) bj = (i ^ 1) < n ? (i ^ 1) : i - 1;        // non-finite boxes: pair neighbours so the loop still ends
             nn[i] = bj;
         }
-        grid.sync();
+        barrier();
         // B: low word = the cluster survives at this position, high word = it is the lower half of a merging pair
         unsigned long long mine = 0ull;
         for (int i = c0 + t; i < c1; i += kBuildThreads) {
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_ploc_all(int n0, const float4
         unsigned long long tot;
         block_excl_scan(mine, &tot);
         if (t == 0) blk_tot[b] = tot;
-        grid.sync();
+        barrier();
         // C
         unsigned long long before = 0ull, all = 0ull;
         for (int k = t; k < nb; k += kBuildThreads) { const unsigned long long v = blk_tot[k]; all += v; if (k < b) before += v; }
@@ -405,7 +416,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_ploc_all(int n0, const float4
         ++rounds;
         if (merges <= 0 || survivors != n - merges) { err = 1; break; }          // same totals in every block: all leave together
         node_base += merges; n = survivors; cur ^= 1;
-        grid.sync();
+        barrier();
     }
     if (b == 0 && t == 0) { ctl->rounds = rounds; ctl->error = err; ctl->ploc_n = n; }
 }
@@ -726,7 +737,7 @@ struct EventTrio {
 };
 
 // co-resident grid of a cooperative build kernel, asked once per process and device
-int coop_grid(int device, const void* kernel, int want_blocks, int* blocks)
+int coop_grid(int device, const void* kernel, int want_blocks, int max_per_sm, int* blocks)
 {
     static std::mutex mu;
     static std::unordered_map<uint64_t, int> cache;
@@ -737,7 +748,7 @@ int coop_grid(int device, const void* kernel, int want_blocks, int* blocks)
         int sms = 148, per_sm = 1;
         DRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBuildThreads, 0));
-        it = cache.emplace(key, sms * std::max(std::min(per_sm, 4), 1)).first;
+        it = cache.emplace(key, sms * std::max(std::min(per_sm, max_per_sm), 1)).first;      // a grid barrier costs more the more blocks take part
     }
     *blocks = std::max(1, std::min(it->second, want_blocks));
     return DRB_OK;
@@ -878,7 +889,7 @@ int build_tree(drb_scene* s, const drb_host_scene* hs, const drb_object* objs_de
                 if (int rc = tmp.alloc(&pmin, nint)) return rc;
                 if (int rc = tmp.alloc(&pmax, nint)) return rc;
                 int blocks = 1;
-                if (int rc = coop_grid(s->device, (const void*)k_ploc_all, (nprims + kBuildThreads - 1) / kBuildThreads, &blocks)) return rc;
+                if (int rc = coop_grid(s->device, (const void*)k_ploc_all, (nprims + kBuildThreads - 1) / kBuildThreads, 2, &blocks)) return rc;
                 if (int rc = tmp.alloc(&btot, (size_t)blocks)) return rc;
                 int n0 = nprims;
                 const float4* c_lmin = lmin; const float4* c_lmax = lmax;
@@ -894,7 +905,7 @@ int build_tree(drb_scene* s, const drb_host_scene* hs, const drb_object* objs_de
             if (int rc = tmp.alloc(&wcounts, (size_t)nprims)) return rc;
             if (int rc = tmp.alloc(&wneed, nint)) return rc;
             int blocks = 1;
-            if (int rc = coop_grid(s->device, (const void*)k_wide_all, (nprims / 2 + kBuildThreads - 1) / kBuildThreads, &blocks)) return rc;
+            if (int rc = coop_grid(s->device, (const void*)k_wide_all, (nprims / 2 + kBuildThreads - 1) / kBuildThreads, 1, &blocks)) return rc;
             if (int rc = tmp.alloc(&wtot, (size_t)blocks)) return rc;
             const int32_t* c_left = tree.left; const int32_t* c_right = tree.right; const float4* c_nmin = tree.node_min; const float4* c_nmax = tree.node_max;
             const float4* c_lmin = lmin; const float4* c_lmax = lmax; const int* c_bounds = d_bounds;
