@@ -30,6 +30,8 @@ _lib = C.CDLL(LIB_PATH)
 OK, ERR_ARG, ERR_IO, ERR_PARSE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 FLAG_ACCUMULATE = 1
 FLAG_EXACT_SAMPLES = 2
+FLAG_DYNAMIC_TILES = 4
+FLAG_SHARD_SAMPLES = 8
 BUILD_LBVH_ONLY = 1
 BUILD_KEEP_DEBUG = 2
 
@@ -148,6 +150,8 @@ _sig("drb_opts_default", None, C.POINTER(Opts))
 _sig("drb_render_device", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _vp, C.POINTER(Stats))
 _sig("drb_render", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _vp, C.POINTER(Stats))
 _sig("drb_render_multi", _i, C.POINTER(C.c_void_p), _i, C.POINTER(Settings), C.POINTER(Opts), _vp, C.POINTER(Stats))
+_sig("drb_render_multi_times", _i, C.POINTER(C.c_float), _i)
+_sig("drb_scene_create_multi", _i, _vp, C.POINTER(C.c_int), _i, _u32, C.POINTER(C.c_void_p))
 _sig("drb_frame_i3", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _i, _vp)
 _sig("drb_trace_ids", _i, _vp, _vp, _vp, _i64, _vp, _vp)
 _sig("drb_primary_rays", _i, _vp, C.POINTER(Settings), C.POINTER(Opts), _u32, _vp, _vp)
@@ -168,7 +172,7 @@ EXPORTED_SYMBOLS = [
     "drb_host_scene_free",
     "drb_host_scene_num_objects", "drb_host_scene_objects", "drb_host_scene_settings",
     "drb_host_scene_num_textures", "drb_host_scene_texture_path", "drb_host_scene_num_skipped", "drb_host_scene_num_renderable",
-    "drb_scene_create_from_device",
+    "drb_scene_create_from_device", "drb_scene_create_multi", "drb_render_multi_times",
     "drb_rts_write", "drb_settings_default", "drb_scene_create", "drb_scene_create_ex", "drb_scene_tree", "drb_scene_wide", "drb_scene_load", "drb_scene_free",
     "drb_scene_settings", "drb_scene_num_prims", "drb_scene_num_objects", "drb_scene_build_info",
     "drb_scene_lbvh", "drb_opts_default", "drb_render_device", "drb_render", "drb_render_multi", "drb_frame_i3",
@@ -202,12 +206,14 @@ def device_count() -> int:
 
 
 def render_multi(scenes: Sequence["Scene"], settings: Optional[Settings] = None, *, seed=0, sample_base=0, sample_count=None,
-                 batch_paths=0, accumulate_into: Optional[np.ndarray] = None) -> Tuple[np.ndarray, Stats]:
-    """One frame over several resident scenes (the same scene on different devices) from this process: interleaved
-    tile sharding, one host thread per handle, merged on the host; bit-identical to Scene.render on one handle."""
-    assert len(scenes) >= 1
+                 batch_paths=0, accumulate_into: Optional[np.ndarray] = None, dynamic=False, shard="tiles") -> Tuple[np.ndarray, Stats]:
+    """One frame over several resident scenes (the same scene on different devices) from this process, one host thread per
+    handle.  shard="tiles" (default): interleaved tiles, bit-identical to Scene.render on one handle; with dynamic=True the
+    tile shards are claimed from a shared queue.  shard="samples": sample ranges, summed in handle order.  With peer access
+    the image lives in one buffer on the first handle's device and the other devices write / are read over NVLink."""
+    assert len(scenes) >= 1 and shard in ("tiles", "samples")
     st = settings if settings is not None else scenes[0].settings
-    flags = 0
+    flags = (FLAG_DYNAMIC_TILES if dynamic else 0) | (FLAG_SHARD_SAMPLES if shard == "samples" else 0)
     if accumulate_into is not None:
         out = np.ascontiguousarray(accumulate_into, dtype=np.float32)
         assert out.shape == (st.height, st.width, 3)
@@ -219,6 +225,22 @@ def render_multi(scenes: Sequence["Scene"], settings: Optional[Settings] = None,
     stats = Stats()
     _check(_lib.drb_render_multi(handles, len(scenes), C.byref(st), C.byref(o), out.ctypes.data, C.byref(stats)))
     return out, stats
+
+
+def render_multi_times() -> list:
+    """device time (ms) each handle spent in this thread's last render_multi call (load-balance measurements)"""
+    buf = (C.c_float * 64)()
+    n = _lib.drb_render_multi_times(buf, 64)
+    return [float(buf[k]) for k in range(min(n, 64))]
+
+
+def create_multi(hs: "HostScene", devices: Sequence[int], build_flags: int = 0) -> list:
+    """The same scene on several devices; the object lines cross PCIe once (each device uploads a share, the devices
+    exchange shares over NVLink) and every device builds its own tree."""
+    devs = (C.c_int * len(devices))(*devices)
+    out = (C.c_void_p * len(devices))()
+    _check(_lib.drb_scene_create_multi(hs.handle, devs, len(devices), build_flags, out))
+    return [Scene(C.c_void_p(out[k])) for k in range(len(devices))]
 
 
 def hash_bytes(data: bytes) -> int:

@@ -1,7 +1,8 @@
 // dogeray-b200: headless drop-in for `raygpu.exe [scene.rts]` (raygpu/kernel.cu:2021-2051, 2486-2516).
 //
-//   dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K] [--out file.bmp|file.ppm]
-//                [--snapshot-every N] [--save-acc file.acc] [--resume file.acc]
+//   dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K | --gpus N | --devices a,b,..]
+//                [--dynamic] [--shard tiles|samples] [--out file.bmp|file.ppm]
+//                [--snapshot-every N] [--save-acc file.acc] [--resume file.acc] [--cache]
 //
 // --snapshot-every N renders N samples per pixel at a time and rewrites the image after every chunk (the headless
 // stand-in for the window's progressive accumulate loop, kernel.cu:2154-2224); --save-acc / --resume checkpoint the
@@ -29,7 +30,7 @@ int main(int argc, char** argv)
     std::string scene_path = "scene.rts", out_path;
     std::string save_acc, resume_acc;
     int spp = -1, depth = -1, w = -1, h = -1, device = 0, snapshot_every = 0;
-    bool use_cache = false;
+    bool use_cache = false, dynamic = false, by_samples = false;
     std::vector<int> devices;                        // --gpus N = 0..N-1, --devices a,b,c = exactly those (repeats allowed)
     unsigned long long seed = 0;
     for (int i = 1; i < argc; ++i) {
@@ -65,12 +66,21 @@ int main(int argc, char** argv)
         else if (a == "--save-acc") save_acc = next("--save-acc");
         else if (a == "--resume") resume_acc = next("--resume");
         else if (a == "--cache") use_cache = true;
+        else if (a == "--dynamic") dynamic = true;
+        else if (a == "--shard") {
+            const std::string v = next("--shard");
+            if (v == "samples") by_samples = true;
+            else if (v != "tiles") { fprintf(stderr, "dogeray-b200: --shard wants tiles or samples\n"); return 2; }
+        }
         else if (a == "--res") { if (sscanf(next("--res"), "%dx%d", &w, &h) != 2) { fprintf(stderr, "dogeray-b200: --res wants WxH\n"); return 2; } }
         else if (a == "-h" || a == "--help") {
             printf("usage: dogeray-b200 [scene.rts] [--spp N] [--depth D] [--res WxH] [--seed S] [--device K | --gpus N | --devices a,b,..]\n"
                    "                    [--out file.bmp|file.ppm]\n"
                    "                    [--snapshot-every N] [--save-acc file.acc] [--resume file.acc] [--cache]\n"
-                   "  --gpus / --devices  one frame over several GPUs from this process (interleaved tiles, same image as one GPU)\n"
+                   "  --gpus / --devices  one frame over several GPUs from this process (interleaved tiles, same image as one GPU;\n"
+                   "                      the scene crosses PCIe once, the GPUs exchange it and the image over NVLink)\n"
+                   "  --dynamic           with several GPUs: tile shards are claimed from a shared queue (load balancing)\n"
+                   "  --shard samples     with several GPUs: split the samples instead of the tiles (sum re-associated)\n"
                    "  --cache  keep the parsed scene in <scene>.drbcache (keyed by a hash of the text) and reuse it\n");
             return 0;
         } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "dogeray-b200: unknown option %s\n", a.c_str()); return 2; }
@@ -87,10 +97,9 @@ int main(int argc, char** argv)
     if (devices.empty()) devices.push_back(device);
     std::vector<drb_scene*> scenes(devices.size(), nullptr);
     printf("Building BVH..\n");
-    for (size_t k = 0; k < devices.size(); ++k)
-        if (drb_scene_create(hs, devices[k], &scenes[k]) != DRB_OK) return fail("cannot create device scene");
+    if (drb_scene_create_multi(hs, devices.data(), (int)devices.size(), 0u, scenes.data()) != DRB_OK) return fail("cannot create device scene");
     drb_scene* scene = scenes[0];
-    if (scenes.size() > 1) printf("%zu device scenes (interleaved tile sharding)\n", scenes.size());
+    if (scenes.size() > 1) printf("%zu device scenes (%s)\n", scenes.size(), by_samples ? "sample sharding" : dynamic ? "tile shards from a shared queue" : "interleaved tile sharding");
     drb_build_info bi;
     drb_scene_build_info(scene, &bi);
     printf("Done! %lld nodes total (upload %.2f ms, build %.2f ms)\n", (long long)bi.nnodes, bi.upload_ms, bi.build_ms);
@@ -134,7 +143,7 @@ int main(int argc, char** argv)
         opts.seed = seed;
         opts.sample_base = (uint32_t)have;
         opts.sample_count = total - done < chunk ? total - done : chunk;
-        opts.flags = DRB_FLAG_ACCUMULATE;
+        opts.flags = DRB_FLAG_ACCUMULATE | (dynamic ? DRB_FLAG_DYNAMIC_TILES : 0u) | (by_samples ? DRB_FLAG_SHARD_SAMPLES : 0u);
         drb_stats stats;
         if (drb_render_multi(scenes.data(), (int)scenes.size(), &st, &opts, accum.data(), &stats) != DRB_OK) return fail("render failed");
         have += opts.sample_count; ms_total += stats.total_ms; rays_total += stats.rays;

@@ -134,6 +134,9 @@ struct drb_scene {
     } while (0)
 
 void drb_render_buffers_free(drb_scene* s);
+// Lets kernels and copies running on device `accessor` address pool memory of device `owner` (NVLink peers); granted once
+// per pair and process.  False when the devices cannot reach each other.
+bool drb_peer_access(int owner, int accessor);
 
 // Device memory for scenes and render buffers.  Blocks come from the device's stream-ordered pool (release
 // threshold raised so nothing goes back to the driver) through an exact-size cache: a scene that is created,

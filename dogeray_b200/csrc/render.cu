@@ -27,6 +27,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -888,11 +889,20 @@ int g_step_min = []() { const char* e = getenv("DOGERAY_B200_STEP_MIN"); int v =
 struct DevBuf {
     void* p = nullptr;
     cudaStream_t st = nullptr;
+    int dev = -1;                       // the block cache is per device: the block goes back with its own device current
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) { cudaStreamSynchronize(st); drb_dev_free(p, st); } }
-    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return drb_dev_alloc(&p, bytes, s); }
+    ~DevBuf()
+    {
+        if (!p) return;
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != dev) cudaSetDevice(dev);
+        cudaStreamSynchronize(st); drb_dev_free(p, st);
+        if (cur != dev && cur >= 0) cudaSetDevice(cur);
+    }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; cudaGetDevice(&dev); return drb_dev_alloc(&p, bytes, s); }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
@@ -1093,27 +1103,46 @@ int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts,
     return DRB_OK;
 }
 
-int drb_render_multi(drb_scene* const* scenes, int nscenes, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats)
+} // extern "C"
+
+// ---- one frame over several handles (devices) from one process ------------------------------------------------------
+namespace {
+
+struct ShardParts { const float* p[32]; };
+
+// dst = (accumulate ? dst : 0) + parts[0] + parts[1] + ... in handle order; the parts live on peer devices (NVLink reads)
+__global__ void __launch_bounds__(256) k_sum_shards(float* __restrict__ dst, ShardParts parts, int nparts, size_t n, int accumulate)
 {
-    if (!scenes || nscenes < 1 || !accum_host) { drb_set_error("drb_render_multi: bad argument"); return DRB_ERR_ARG; }
-    for (int k = 0; k < nscenes; ++k)
-        if (!scenes[k]) { drb_set_error("drb_render_multi: scene %d is null", k); return DRB_ERR_ARG; }
-    if (int rc = check_settings(settings)) return rc;
-    drb_opts base; if (opts) base = *opts; else drb_opts_default(&base);
-    if (base.stream) { drb_set_error("drb_render_multi: opts->stream must be NULL (each handle renders on its own stream)"); return DRB_ERR_ARG; }
-    if (nscenes == 1) { base.tile_rank = 0; base.tile_count = 1; return drb_render(scenes[0], settings, &base, accum_host, stats); }
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = accumulate ? dst[i] : 0.0f;
+    for (int k = 0; k < nparts; ++k) v = v + parts.p[k][i];
+    dst[i] = v;
+}
+
+thread_local std::vector<float> t_multi_ms;           // per-handle device time of this thread's last drb_render_multi
+
+void add_stats(drb_stats& into, const drb_stats& t)
+{
+    into.paths += t.paths; into.rays += t.rays;
+    into.trace_launches += t.trace_launches; into.kernel_launches += t.kernel_launches;
+    into.trace_ms += t.trace_ms; into.total_ms += t.total_ms;
+}
+
+// the pre-P2P path: every shard starts from the caller's image in host memory and changes only its own tiles, the shards are
+// merged on the host by pixel ownership.  Used when some handle's device cannot reach the first handle's device.
+int render_multi_through_host(drb_scene* const* scenes, int nscenes, const drb_settings* settings, const drb_opts& base, float* accum_host,
+                              std::vector<drb_stats>& sts)
+{
     const int W = settings->width, H = settings->height;
     const size_t n = (size_t)W * H * 3;
-    // Every shard starts from the caller's image and changes only its own tiles, so picking each pixel from the
-    // shard that owns it reproduces the one-handle result bit for bit, with or without DRB_FLAG_ACCUMULATE.
     std::vector<std::vector<float>> shard((size_t)nscenes - 1);
     std::vector<int> rcs((size_t)nscenes, DRB_OK);
     std::vector<std::string> errs((size_t)nscenes);
-    std::vector<drb_stats> sts((size_t)nscenes);
     auto work = [&](int k, float* dst) {
         drb_opts o = base;
+        o.flags &= ~(DRB_FLAG_DYNAMIC_TILES | DRB_FLAG_SHARD_SAMPLES);
         o.tile_rank = (uint32_t)k; o.tile_count = (uint32_t)nscenes;
-        memset(&sts[(size_t)k], 0, sizeof(drb_stats));
         rcs[(size_t)k] = drb_render(scenes[k], settings, &o, dst, &sts[(size_t)k]);
         if (rcs[(size_t)k] != DRB_OK) errs[(size_t)k] = drb_last_error();       // the message is thread-local
     };
@@ -1135,17 +1164,139 @@ int drb_render_multi(drb_scene* const* scenes, int nscenes, const drb_settings* 
             const size_t len = (size_t)std::min(8, W - tx * 8) * 3;
             memcpy(accum_host + at, shard[owner - 1].data() + at, len * sizeof(float));
         }
-    if (stats) {
-        memset(stats, 0, sizeof *stats);
-        for (const drb_stats& t : sts) {
-            stats->paths += t.paths; stats->rays += t.rays;
-            stats->trace_launches += t.trace_launches; stats->kernel_launches += t.kernel_launches;
-            stats->trace_ms = std::max(stats->trace_ms, t.trace_ms);            // the handles run side by side
-            stats->total_ms = std::max(stats->total_ms, t.total_ms);
-        }
-    }
     return DRB_OK;
 }
+
+} // namespace
+
+extern "C" int drb_render_multi_times(float* ms, int n)
+{
+    for (int k = 0; k < n && k < (int)t_multi_ms.size(); ++k) ms[k] = t_multi_ms[(size_t)k];
+    return (int)t_multi_ms.size();
+}
+
+extern "C" int drb_render_multi(drb_scene* const* scenes, int nscenes, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats)
+{
+    if (!scenes || nscenes < 1 || !accum_host) { drb_set_error("drb_render_multi: bad argument"); return DRB_ERR_ARG; }
+    for (int k = 0; k < nscenes; ++k)
+        if (!scenes[k]) { drb_set_error("drb_render_multi: scene %d is null", k); return DRB_ERR_ARG; }
+    if (int rc = check_settings(settings)) return rc;
+    drb_opts base; if (opts) base = *opts; else drb_opts_default(&base);
+    if (base.stream) { drb_set_error("drb_render_multi: opts->stream must be NULL (each handle renders on its own stream)"); return DRB_ERR_ARG; }
+    const bool by_samples = (base.flags & DRB_FLAG_SHARD_SAMPLES) != 0, dynamic = (base.flags & DRB_FLAG_DYNAMIC_TILES) != 0 && !by_samples;
+    if (by_samples && nscenes > 32) { drb_set_error("drb_render_multi: at most 32 handles with DRB_FLAG_SHARD_SAMPLES"); return DRB_ERR_ARG; }
+    t_multi_ms.assign((size_t)nscenes, 0.0f);
+    std::vector<drb_stats> sts((size_t)nscenes);
+    for (auto& t : sts) memset(&t, 0, sizeof t);
+    auto finish_stats = [&]() {
+        if (stats) memset(stats, 0, sizeof *stats);
+        for (int k = 0; k < nscenes; ++k) {
+            t_multi_ms[(size_t)k] = sts[(size_t)k].total_ms;
+            if (!stats) continue;
+            stats->paths += sts[(size_t)k].paths; stats->rays += sts[(size_t)k].rays;
+            stats->trace_launches += sts[(size_t)k].trace_launches; stats->kernel_launches += sts[(size_t)k].kernel_launches;
+            stats->trace_ms = std::max(stats->trace_ms, sts[(size_t)k].trace_ms);            // the handles run side by side
+            stats->total_ms = std::max(stats->total_ms, sts[(size_t)k].total_ms);
+        }
+    };
+    if (nscenes == 1) {
+        base.flags &= ~(DRB_FLAG_DYNAMIC_TILES | DRB_FLAG_SHARD_SAMPLES);
+        base.tile_rank = 0; base.tile_count = 1;
+        const int rc = drb_render(scenes[0], settings, &base, accum_host, &sts[0]);
+        if (rc == DRB_OK) finish_stats();
+        return rc;
+    }
+    const int W = settings->width, H = settings->height;
+    const size_t n = (size_t)W * H * 3;
+    drb_scene* first = scenes[0];
+    const int dev0 = first->device;
+    // tiles: every handle's kernels must be able to WRITE the image on dev0; samples: dev0's kernel must READ the parts
+    bool peers = true;
+    for (int k = 1; k < nscenes; ++k)
+        peers = peers && (by_samples ? drb_peer_access(scenes[k]->device, dev0) : drb_peer_access(dev0, scenes[k]->device));
+    if (!peers && !by_samples) {
+        const int rc = render_multi_through_host(scenes, nscenes, settings, base, accum_host, sts);
+        if (rc == DRB_OK) finish_stats();
+        return rc;
+    }
+    DRB_CUDA(cudaSetDevice(dev0));
+    DevBuf image;                                           // THE image, on the first handle's device
+    DRB_CUDA(image.alloc(n * sizeof(float), first->stream));
+    float* d_image = image.as<float>();
+    const bool accumulate = (base.flags & DRB_FLAG_ACCUMULATE) != 0;
+    if (accumulate) DRB_CUDA(cudaMemcpyAsync(d_image, accum_host, n * sizeof(float), cudaMemcpyHostToDevice, first->stream));
+    DRB_CUDA(cudaStreamSynchronize(first->stream));        // the other devices' streams may touch it from here on
+
+    std::vector<int> rcs((size_t)nscenes, DRB_OK);
+    std::vector<std::string> errs((size_t)nscenes);
+    std::vector<DevBuf> parts((size_t)(by_samples ? nscenes : 0));
+    std::atomic<uint32_t> next_shard{ 0 };
+    const uint32_t nshards = dynamic ? 4u * (uint32_t)nscenes : (uint32_t)nscenes;
+    const uint32_t total_samples = requested_samples(base, *settings);
+    auto fail = [&](int k, int rc) { rcs[(size_t)k] = rc; errs[(size_t)k] = drb_last_error(); };
+    auto work = [&](int k) {
+        drb_scene* sc = scenes[k];
+        drb_opts o = base;
+        o.flags &= ~(DRB_FLAG_DYNAMIC_TILES | DRB_FLAG_SHARD_SAMPLES);
+        if (cudaSetDevice(sc->device) != cudaSuccess) { drb_set_error("cudaSetDevice(%d) failed", sc->device); return fail(k, DRB_ERR_CUDA); }
+        if (by_samples) {
+            // sample range k of nscenes (the same split as distributed.shard_samples), into this device's own buffer
+            const uint32_t q = total_samples / (uint32_t)nscenes, r = total_samples % (uint32_t)nscenes;
+            o.sample_base = base.sample_base + (uint32_t)k * q + std::min<uint32_t>((uint32_t)k, r);
+            o.sample_count = q + ((uint32_t)k < r ? 1u : 0u);
+            o.flags = (o.flags & ~DRB_FLAG_ACCUMULATE) | DRB_FLAG_EXACT_SAMPLES;
+            o.tile_rank = 0; o.tile_count = 1;
+            if (parts[(size_t)k].alloc(n * sizeof(float), sc->stream) != cudaSuccess) { drb_set_error("out of device memory for a sample shard"); return fail(k, DRB_ERR_NOMEM); }
+            if (int rc = render_core(sc, settings, &o, W, H, 1, parts[(size_t)k].as<float>(), &sts[(size_t)k])) return fail(k, rc);
+            return;
+        }
+        // tiles: claim shards (static: exactly shard k) and resolve them straight into the image on dev0
+        for (;;) {
+            const uint32_t j = dynamic ? next_shard.fetch_add(1u) : (uint32_t)k;
+            if (j >= nshards) break;
+            o.tile_rank = j; o.tile_count = nshards;
+            drb_stats t;
+            if (int rc = render_core(sc, settings, &o, W, H, 1, d_image, &t)) return fail(k, rc);
+            add_stats(sts[(size_t)k], t);
+            if (!dynamic) break;
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int k = 1; k < nscenes; ++k) pool.emplace_back(work, k);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    for (int k = 0; k < nscenes; ++k)
+        if (rcs[(size_t)k] != DRB_OK) { drb_set_error("drb_render_multi: scene %d: %s", k, errs[(size_t)k].c_str()); return rcs[(size_t)k]; }
+    DRB_CUDA(cudaSetDevice(dev0));
+    if (by_samples) {
+        if (peers) {
+            ShardParts sp;
+            for (int k = 0; k < nscenes; ++k) sp.p[k] = parts[(size_t)k].as<float>();
+            k_sum_shards<<<(unsigned)((n + 255) / 256), 256, 0, first->stream>>>(d_image, sp, nscenes, n, accumulate ? 1 : 0);
+            DRB_CUDA(cudaGetLastError());
+            DRB_CUDA(cudaMemcpyAsync(accum_host, d_image, n * sizeof(float), cudaMemcpyDeviceToHost, first->stream));
+            DRB_CUDA(cudaStreamSynchronize(first->stream));
+        } else {
+            // no peer access: the parts come back one by one and are added on the host, in the same order
+            std::vector<float> tmp(n);
+            for (int k = 0; k < nscenes; ++k) {
+                DRB_CUDA(cudaSetDevice(scenes[k]->device));
+                DRB_CUDA(cudaMemcpy(tmp.data(), parts[(size_t)k].as<float>(), n * sizeof(float), cudaMemcpyDeviceToHost));
+                if (k == 0 && !accumulate) memcpy(accum_host, tmp.data(), n * sizeof(float));
+                else for (size_t i = 0; i < n; ++i) accum_host[i] = accum_host[i] + tmp[i];
+            }
+        }
+    } else {
+        DRB_CUDA(cudaMemcpyAsync(accum_host, d_image, n * sizeof(float), cudaMemcpyDeviceToHost, first->stream));
+        DRB_CUDA(cudaStreamSynchronize(first->stream));
+    }
+    finish_stats();
+    return DRB_OK;
+}
+
+extern "C" {
 
 int drb_frame_i3(drb_scene* s, const drb_settings* settings, const drb_opts* opts, int divisor, int32_t* out)
 {

@@ -23,6 +23,7 @@
 #include <chrono>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace cg = cooperative_groups;
@@ -684,6 +685,38 @@ void drb_dev_free(void* p, cudaStream_t st)
     cudaFreeAsync(p, st);
 }
 
+bool drb_peer_access(int owner, int accessor)
+{
+    if (owner == accessor) return true;
+    static std::mutex mu;
+    static std::unordered_map<int, bool> done;                  // owner * 4096 + accessor -> usable
+    std::lock_guard<std::mutex> g(mu);
+    const int key = owner * 4096 + accessor;
+    auto it = done.find(key);
+    if (it != done.end()) return it->second;
+    bool ok = false;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, accessor, owner) == cudaSuccess && can) {
+        // everything here comes from the stream-ordered pool, whose visibility is set per pool ...
+        cudaMemPool_t pool;
+        cudaMemAccessDesc d;
+        memset(&d, 0, sizeof d);
+        d.location.type = cudaMemLocationTypeDevice; d.location.id = accessor; d.flags = cudaMemAccessFlagsProtReadWrite;
+        ok = cudaDeviceGetDefaultMemPool(&pool, owner) == cudaSuccess && cudaMemPoolSetAccess(pool, &d, 1) == cudaSuccess;
+        // ... and classic peer access as well, so that peer copies take the direct NVLink path
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cudaSetDevice(accessor) == cudaSuccess) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+        }
+        cudaSetDevice(cur);
+    }
+    cudaGetLastError();
+    done[key] = ok;
+    return ok;
+}
+
 extern "C" int drb_trim(int device)
 {
     DRB_CUDA(cudaSetDevice(device));
@@ -1058,6 +1091,90 @@ int drb_scene_create_from_device(const drb_host_scene* hs, int device, uint32_t 
     if (rc != DRB_OK) { std::string keep = drb_last_error(); drb_scene_free(s); drb_set_error("%s", keep.c_str()); return rc; }
     if (s->settings.backtex >= s->ntextures) s->settings.backtex = -1;
     *out = s;
+    return DRB_OK;
+}
+
+int drb_scene_create_multi(const drb_host_scene* hs, const int* devices, int ndevices, uint32_t build_flags, drb_scene** out)
+{
+    if (!hs || !devices || ndevices < 1 || !out) { drb_set_error("drb_scene_create_multi: bad argument"); return DRB_ERR_ARG; }
+    for (int k = 0; k < ndevices; ++k) out[k] = nullptr;
+    if (ndevices == 1) return drb_scene_create_ex(hs, devices[0], build_flags, &out[0]);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); drb_set_error("no CUDA device available (dogeray_b200 has no CPU path)"); return DRB_ERR_CUDA; }
+    for (int k = 0; k < ndevices; ++k)
+        if (devices[k] < 0 || devices[k] >= ndev) { drb_set_error("device %d out of range (0..%d)", devices[k], ndev - 1); return DRB_ERR_ARG; }
+    drb_host_scene_summarise(hs);                                   // before the threads: the cached counts are not thread-safe
+    const size_t nobj = hs->objects.size();
+    if (nobj && !hs->pinned) {
+        if (cudaHostRegister((void*)hs->objects.data(), nobj * sizeof(drb_object), cudaHostRegisterPortable) == cudaSuccess) hs->pinned = true;
+        else cudaGetLastError();
+    }
+    // share k = object lines [k * chunk, (k + 1) * chunk): uploaded by device k, pulled by all the others
+    const size_t chunk = (nobj + (size_t)ndevices - 1) / (size_t)ndevices;
+    struct Side { drb_object* buf = nullptr; cudaStream_t st = nullptr; cudaEvent_t uploaded = nullptr, pulled = nullptr; int rc = DRB_OK; std::string err; };
+    std::vector<Side> side((size_t)ndevices);
+    auto share = [&](int k, size_t* lo, size_t* hi) { *lo = std::min(nobj, (size_t)k * chunk); *hi = std::min(nobj, *lo + chunk); };
+    // phase 1 (sequential, cheap): buffers, streams, events, and each device's own share on its way
+    for (int k = 0; k < ndevices; ++k) {
+        Side& sd = side[(size_t)k];
+        auto bad = [&](const char* what) { sd.rc = DRB_ERR_CUDA; sd.err = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()); };
+        if (cudaSetDevice(devices[k]) != cudaSuccess) { bad("cudaSetDevice"); break; }
+        if (retain_pool(devices[k]) != DRB_OK) { sd.rc = DRB_ERR_CUDA; sd.err = drb_last_error(); break; }
+        if (cudaStreamCreateWithFlags(&sd.st, cudaStreamNonBlocking) != cudaSuccess) { bad("cudaStreamCreate"); break; }
+        if (cudaEventCreateWithFlags(&sd.uploaded, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&sd.pulled, cudaEventDisableTiming) != cudaSuccess) { bad("cudaEventCreate"); break; }
+        if (drb_dev_alloc((void**)&sd.buf, std::max<size_t>(nobj, 1) * sizeof(drb_object), sd.st) != cudaSuccess) { bad("device memory for the object lines"); break; }
+        size_t lo, hi; share(k, &lo, &hi);
+        if (hi > lo && cudaMemcpyAsync(sd.buf + lo, hs->objects.data() + lo, (hi - lo) * sizeof(drb_object), cudaMemcpyHostToDevice, sd.st) != cudaSuccess) { bad("upload"); break; }
+        if (cudaEventRecord(sd.uploaded, sd.st) != cudaSuccess) { bad("cudaEventRecord"); break; }
+    }
+    bool ok = true;
+    for (const Side& sd : side) ok = ok && sd.rc == DRB_OK;
+    // phase 2: every device pulls the other shares from the device that uploaded them (NVLink where there is peer access,
+    // staged by the driver otherwise), then builds; one host thread per device
+    if (ok) {
+        for (int k = 0; k < ndevices; ++k)
+            for (int j = 0; j < ndevices; ++j) drb_peer_access(devices[j], devices[k]);
+        auto work = [&](int k) {
+            Side& sd = side[(size_t)k];
+            auto bad = [&](const char* what) { sd.rc = DRB_ERR_CUDA; sd.err = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()); };
+            if (cudaSetDevice(devices[k]) != cudaSuccess) return bad("cudaSetDevice");
+            for (int d = 1; d < ndevices; ++d) {
+                const int j = (k + d) % ndevices;                   // staggered, so the pulls do not all hit the same source at once
+                size_t lo, hi; share(j, &lo, &hi);
+                if (hi <= lo) continue;
+                if (cudaStreamWaitEvent(sd.st, side[(size_t)j].uploaded, 0) != cudaSuccess) return bad("cudaStreamWaitEvent");
+                if (cudaMemcpyPeerAsync(sd.buf + lo, devices[k], side[(size_t)j].buf + lo, devices[j], (hi - lo) * sizeof(drb_object), sd.st) != cudaSuccess) return bad("peer copy");
+            }
+            if (cudaEventRecord(sd.pulled, sd.st) != cudaSuccess) return bad("cudaEventRecord");
+            sd.rc = drb_scene_create_from_device(hs, devices[k], build_flags, sd.buf, sd.st, &out[k]);
+            if (sd.rc != DRB_OK) sd.err = drb_last_error();
+        };
+        std::vector<std::thread> pool;
+        for (int k = 1; k < ndevices; ++k) pool.emplace_back(work, k);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    // a share may be freed only after every device has pulled it
+    for (int k = 0; k < ndevices; ++k) {
+        Side& sd = side[(size_t)k];
+        if (cudaSetDevice(devices[k]) != cudaSuccess) { cudaGetLastError(); continue; }
+        for (int j = 0; j < ndevices; ++j)
+            if (side[(size_t)j].pulled) cudaEventSynchronize(side[(size_t)j].pulled);
+        if (sd.st) cudaStreamSynchronize(sd.st);
+        if (sd.buf) drb_dev_free(sd.buf, sd.st);
+        if (sd.uploaded) cudaEventDestroy(sd.uploaded);
+        if (sd.pulled) cudaEventDestroy(sd.pulled);
+        if (sd.st) cudaStreamDestroy(sd.st);
+    }
+    cudaGetLastError();
+    for (int k = 0; k < ndevices; ++k)
+        if (side[(size_t)k].rc != DRB_OK) {
+            const int rc = side[(size_t)k].rc;
+            const std::string msg = side[(size_t)k].err;
+            for (int j = 0; j < ndevices; ++j) { if (out[j]) drb_scene_free(out[j]); out[j] = nullptr; }
+            drb_set_error("drb_scene_create_multi: device %d: %s", devices[k], msg.c_str());
+            return rc;
+        }
     return DRB_OK;
 }
 

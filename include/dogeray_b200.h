@@ -137,6 +137,10 @@ int drb_scene_create_ex(const drb_host_scene* hs, int device, uint32_t build_fla
  * supplies settings, textures and counts; the array is only read during the call. */
 int drb_scene_create_from_device(const drb_host_scene* hs, int device, uint32_t build_flags, const void* objects_dev, void* stream,
                                  drb_scene** out);
+/* The same scene on `ndevices` devices (out[k] on devices[k]; a device may be listed more than once).  The object lines
+ * cross PCIe ONCE in total: device k uploads lines [k*chunk, (k+1)*chunk), the devices then pull each other's shares over
+ * NVLink (peer copies), and every device builds its own tree.  On failure nothing is left allocated. */
+int drb_scene_create_multi(const drb_host_scene* hs, const int* devices, int ndevices, uint32_t build_flags, drb_scene** out);
 /* convenience: drb_host_scene_load + drb_scene_create */
 int drb_scene_load(const char* rts_path, const char* tex_dir, int device, drb_scene** out);
 void drb_scene_free(drb_scene* s);
@@ -211,13 +215,27 @@ int drb_render_device(drb_scene* s, const drb_settings* settings, const drb_opts
 /* Same with a HOST accumulation buffer (synchronous; includes the device->host copy). */
 int drb_render(drb_scene* s, const drb_settings* settings, const drb_opts* opts, float* accum_host, drb_stats* stats);
 /* One frame over several resident scenes -- normally the same scene created on different devices (SURVEY.md
- * 8(b)3 "device list", 8(e)) -- from one process: one host thread per handle, handle k traces the 8x4-pixel tiles t
- * with t % nscenes == k (opts->tile_rank / tile_count are overridden), and the shards are merged on the host.
- * Pixel sets are disjoint, so the image is bit-identical to drb_render on a single handle, with or without
- * DRB_FLAG_ACCUMULATE.  opts->stream must be NULL.  `stats`: paths, rays and launches are summed, times are the
- * maximum over handles.  (torch.distributed callers use drb_render_device + one reduce instead) */
+ * 8(b)3 "device list", 8(e); drb_scene_create_multi) -- from one process, one host thread per handle.
+ *   default           interleaved tiles: handle k traces the 8x4-pixel tiles t with t % nscenes == k (opts->tile_rank /
+ *                     tile_count are overridden).  Pixel sets are disjoint, so the image is bit-identical to drb_render on
+ *                     a single handle, with or without DRB_FLAG_ACCUMULATE.
+ *   DRB_FLAG_DYNAMIC_TILES   the tiles are cut into 4 x nscenes interleaved shards that the handles claim from a shared
+ *                     atomic queue as they become free: a slower or busier GPU takes fewer shards.  Same bits as above.
+ *   DRB_FLAG_SHARD_SAMPLES   handle k traces sample range k of nscenes (as the torch.distributed path does); the partial
+ *                     sums are added in handle order, so the image equals the one-handle image up to float re-association.
+ * The image lives in ONE device buffer on scenes[0]'s device.  Where the devices have peer access (NVLink) the other
+ * handles' resolve kernels write their tiles straight into it -- the gather rides on the last kernel of the render, there
+ * is no separate exchange step -- and sample shards are summed by one kernel on that device reading the peers' buffers.
+ * One host <-> device copy of the image per call in total.  Without peer access the shards are merged through host
+ * memory.  opts->stream must be NULL.  `stats`: paths, rays and launches are summed, times are the maximum over handles.
+ * (torch.distributed callers use drb_render_device + one NCCL reduce instead) */
+#define DRB_FLAG_DYNAMIC_TILES 4u
+#define DRB_FLAG_SHARD_SAMPLES 8u
 int drb_render_multi(drb_scene* const* scenes, int nscenes, const drb_settings* settings, const drb_opts* opts,
                      float* accum_host, drb_stats* stats);
+/* Per-handle device time (ms) of the last drb_render_multi call on this thread, handle order, up to `n` entries; returns how
+ * many handles that call had.  For load-balance measurements. */
+int drb_render_multi_times(float* ms, int n);
 
 /* Exact output contract of CudaStarter (kernel.cu:2562-2669, Kernel :998-1093): out[(x*H + y)*3 + c] =
  * trunc(255 * mean radiance) for x < W/divisor/8*8, y < H/divisor/8*8, other entries untouched.

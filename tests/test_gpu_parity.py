@@ -539,8 +539,9 @@ def test_tile_sharding_is_bit_identical_to_the_whole_image():
 
 
 def test_render_multi_over_several_handles_is_bit_identical_to_one_handle():
-    """drb_render_multi: one host thread per handle, interleaved tiles, merged on the host.  Two and three handles on
-    device 0 stand in for two and three GPUs (the code path is the same; only the device number differs)."""
+    """drb_render_multi: one host thread per handle, interleaved tiles resolved straight into one device image.  Two and
+    three handles on device 0 stand in for two and three GPUs (same code path; test_render_multi_on_two_devices runs it
+    across real peers)."""
     objs, st = synth.heightfield_scene(n=24, width=83, height=47, spp=6, max_depth=5)      # ragged right and bottom tiles
     hs = drb.HostScene.from_objects(objs, st)
     scenes = [drb.Scene.from_host(hs) for _ in range(3)]
@@ -559,6 +560,24 @@ def test_render_multi_over_several_handles_is_bit_identical_to_one_handle():
     # small batches inside every shard
     c, _ = drb.render_multi(scenes, st, seed=21, batch_paths=4096)
     assert np.array_equal(c, full)
+    # tile shards claimed from the shared queue: whoever renders a shard, the bits are the same
+    for n in (2, 3):
+        d, sd = drb.render_multi(scenes[:n], st, seed=21, dynamic=True)
+        assert np.array_equal(d, full) and sd.rays == sf.rays and sd.paths == sf.paths
+        assert len(drb.render_multi_times()) == n
+    d, _ = drb.render_multi(scenes[:2], st, seed=21, sample_base=0, sample_count=3, dynamic=True)
+    d, _ = drb.render_multi(scenes[:2], st, seed=21, sample_base=3, sample_count=3, accumulate_into=d, dynamic=True)
+    assert np.array_equal(d, a)
+    # sample shards: handle k traces sample range k, the parts are added in handle order by one kernel
+    e, se = drb.render_multi(scenes, st, seed=21, shard="samples")
+    assert se.rays == sf.rays and se.paths == sf.paths
+    parts = [scenes[0].render(st, seed=21, sample_base=2 * k, sample_count=2)[0] for k in range(3)]
+    assert np.array_equal(e, (parts[0] + parts[1]) + parts[2])
+    assert np.allclose(e, full, rtol=0, atol=1e-5)
+    e2, _ = drb.render_multi(scenes[:2], st, seed=21, shard="samples", accumulate_into=full.copy())
+    assert np.allclose(e2, 2 * full, rtol=0, atol=2e-5)
+    g, sg = drb.render_multi(scenes, st.replace(spp=2), seed=21, shard="samples")          # fewer samples than handles: an empty share
+    assert sg.paths == 83 * 47 * 2 and np.allclose(g, parts[0], rtol=0, atol=1e-6)
     with pytest.raises(drb.DogerayError):
         bad = drb.Settings.from_buffer_copy(bytes(st)); bad.width = 0
         drb.render_multi(scenes[:2], bad)
@@ -576,4 +595,18 @@ def test_render_multi_on_two_devices():
     assert np.array_equal(full, other)                                     # the build and the frame do not depend on the device
     img, sm = drb.render_multi([s0, s1], st, seed=5)
     assert np.array_equal(img, full) and sm.rays == sf.rays
+    # the same scene made by ONE sharded upload + peer exchange; dynamic tiles and sample shards across real peers
+    ndev = min(drb.device_count(), 4)
+    scenes = drb.create_multi(hs, list(range(ndev)))
+    w0 = s0.wide()
+    for sc in scenes:
+        w = sc.wide()
+        assert np.array_equal(w["child"], w0["child"]) and np.array_equal(w["boxes"], w0["boxes"])
+    for kw in (dict(), dict(dynamic=True)):
+        img, sm = drb.render_multi(scenes, st, seed=5, **kw)
+        assert np.array_equal(img, full) and sm.rays == sf.rays
+    img, sm = drb.render_multi(scenes, st, seed=5, shard="samples")
+    assert sm.rays == sf.rays and np.allclose(img, full, rtol=0, atol=1e-5)
+    again, _ = drb.render_multi(scenes, st, seed=5, shard="samples")
+    assert np.array_equal(again, img)                                      # fixed summation order
 

@@ -1,29 +1,67 @@
-"""On a box with >= 2 GPUs: the CLI's --gpus 2 against --gpus 1 on the 1 M-triangle scene (byte-identical BMP,
-wall-clock and device times as the CLI prints them).  python tools/cli_multi_check.py [spp]"""
+"""The in-process multi-GPU path (drb_scene_create_multi + drb_render_multi) on a box with several GPUs:
+
+    python tools/cli_multi_check.py [spp] [grid1m|city10m]
+
+  * the CLI at --gpus 1/2/4/8 (static tiles, --dynamic, --shard samples): byte-identical BMPs for the tile modes, wall
+    clock and the device time the CLI prints;
+  * per-handle device times of one static-tile frame through the library (drb_render_multi_times): the static imbalance
+    max/mean - 1, i.e. what dynamic balancing could win on equal GPUs."""
+import json
 import os
 import subprocess
 import sys
 import tempfile
 import time
 
+import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dogeray_b200 as drb
 from dogeray_b200 import synth
 
 spp = sys.argv[1] if len(sys.argv) > 1 else "64"
+which = sys.argv[2] if len(sys.argv) > 2 else "grid1m"
 cli = os.path.join(os.path.dirname(drb.__file__), "dogeray-b200")
 d = tempfile.mkdtemp(prefix="drb_cli_")
-objs, st = synth.instanced_grid_scene()
+objs, st = synth.city_scene() if which == "city10m" else synth.instanced_grid_scene()
+res = "%dx%d" % (st.width, st.height)
 drb.write_rts(os.path.join(d, "scene.rts"), st, objs)
-out = {}
-for n in range(1, drb.device_count() + 1):
-    if n not in (1, 2, 4, 8):
+ndev = drb.device_count()
+out, rows = {}, []
+for n in (1, 2, 4, 8):
+    if n > ndev:
         continue
-    t = time.time()
-    p = subprocess.run([cli, "scene.rts", "--spp", spp, "--gpus", str(n), "--cache", "--out", "g%d.bmp" % n], capture_output=True, text=True, cwd=d)
-    wall = time.time() - t
-    assert p.returncode == 0, p.stdout + p.stderr
-    out[n] = open(os.path.join(d, "g%d.bmp" % n), "rb").read()
-    print("gpus=%d wall %.2f s | %s" % (n, wall, " | ".join(l for l in p.stdout.splitlines() if l.startswith(("Time", "scene cache", "Done")))), flush=True)
-    assert out[n] == out[1], "image differs from the 1-GPU image"
-print("all images byte-identical:", sorted(out))
+    for mode, extra in (("tiles", []), ("dynamic", ["--dynamic"]), ("samples", ["--shard", "samples"])):
+        if n == 1 and mode != "tiles":
+            continue
+        name = "g%d_%s.bmp" % (n, mode)
+        t = time.time()
+        p = subprocess.run([cli, "scene.rts", "--spp", spp, "--gpus", str(n), "--cache", "--out", name] + extra, capture_output=True, text=True, cwd=d)
+        wall = time.time() - t
+        assert p.returncode == 0, p.stdout + p.stderr
+        out[(n, mode)] = open(os.path.join(d, name), "rb").read()
+        line = [l for l in p.stdout.splitlines() if l.startswith("Time")][0]
+        ms = float(line.split()[2])
+        mrays = float(line.split()[-2])
+        rows.append({"scene": which, "res": res, "spp": int(spp), "gpus": n, "mode": mode, "device_ms": ms, "mrays_s": mrays, "wall_s": round(wall, 2),
+                     "identical_to_1gpu": out[(n, mode)] == out[(1, "tiles")]})
+        print(json.dumps(rows[-1]), flush=True)
+        if mode != "samples":
+            assert out[(n, mode)] == out[(1, "tiles")], "image differs from the 1-GPU image"
+# static imbalance through the library
+hs = drb.HostScene.load(os.path.join(d, "scene.rts"), d, cache=True)
+for n in (2, 4, 8):
+    if n > ndev:
+        continue
+    scenes = drb.create_multi(hs, list(range(n)))
+    s1 = st.replace(spp=int(spp))
+    drb.render_multi(scenes, s1, seed=0)                             # warm-up (buffers)
+    _, sm = drb.render_multi(scenes, s1, seed=0)
+    times = drb.render_multi_times()
+    _, sd = drb.render_multi(scenes, s1, seed=0, dynamic=True)
+    dtimes = drb.render_multi_times()
+    print(json.dumps({"scene": which, "gpus": n, "static_ms_per_handle": [round(t, 2) for t in times], "static_imbalance": max(times) / (sum(times) / n) - 1,
+                      "static_frame_ms": max(times), "dynamic_busy_ms_per_handle": [round(t, 2) for t in dtimes], "dynamic_frame_ms": max(dtimes)}), flush=True)
+    for sc in scenes:
+        sc.close()
+print("done")
