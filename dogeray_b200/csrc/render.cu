@@ -7,11 +7,12 @@
 //
 //   k_generate   camera rays for every path slot of the batch                (kernel.cu:1016-1076)
 //   repeat max_depth times:
-//     k_trace    persistent warps pull 32 rays at a time from the ray queue, closest hit through the
-//                64 B two-box nodes with a per-thread stack, Moeller-Trumbore in the reference's
-//                operation order                                             (kernel.cu:468-512, 277-313)
-//     k_shade    normal / texture / material scatter or termination; survivors are appended to the
-//                next ray queue with one atomic per warp (ballot + popc)     (kernel.cu:787-982)
+//     k_trace    persistent warps, every lane refills itself from the ray queue; closest hit through the 64 B
+//                four-wide nodes (16-bit quantised child boxes, two 256-bit loads) with a shared-memory stack,
+//                Moeller-Trumbore in the reference's operation order        (kernel.cu:468-512, 277-313)
+//     k_shade    normal / texture / material scatter or termination; the unit-sphere rejection sampling of a
+//                warp's rays is pooled and drained with per-lane refill; survivors are appended to the next
+//                ray queue in ray order, one atomic per warp iteration      (kernel.cu:787-982)
 //   k_resolve    per pixel, sum the batch's samples in sample order into the accumulator
 //
 // Terminated paths write their radiance to contrib[slot] exactly once, so the image is a
@@ -436,153 +437,248 @@ DRB_D f3 environment(const DevScene& sc, const FrameParams& fp, f3 raydir)
     return mk3(omt) * mk3(1.0f) + mk3(t) * mk3(0.5f, 0.7f, 1.0f);
 }
 
+// The unit-sphere rejection loop (kernel.cu:640-647) is ~60 % of the shading instructions and, run per ray inside a warp,
+// keeps ~10 of 32 lanes busy: the warp waits for its unluckiest lane while each attempt costs a Philox block.  So a warp
+// takes kShadeRays consecutive rays per iteration and works in three stages through shared memory:
+//   1  (full width, once per 32 rays) loads, miss / emissive termination, normal, textures, material; a ray that scatters
+//      leaves a record: its finished successor (mirror, glass), or what stage 3 needs plus a sampling request;
+//   2  the requests form a pool that the 32 lanes drain with per-lane refill: a lane makes one attempt per iteration and
+//      takes the next request as soon as its own is accepted, so the lanes stay busy until the pool is dry.  ONE Philox
+//      call site serves the block a stream resumes in and the blocks after it;
+//   3  (full width) finishes the scatter from record + sample and appends the successors IN RAY ORDER with one atomic
+//      for the whole group -- the next bounce sees the same queue order as a ray-per-lane pass would give it.
+// Every path consumes exactly the words it always did (draw n of a path is word n of its Philox stream), so the image
+// does not change by a bit.
+#ifndef DRB_SHADE_GROUPS
+#define DRB_SHADE_GROUPS 2
+#endif
+constexpr int kShadeGroups = DRB_SHADE_GROUPS;          // 32-ray groups per warp iteration
+constexpr int kShadeRays = 32 * kShadeGroups;
+enum { REC_HX = 0, REC_HY, REC_HZ, REC_VX, REC_VY, REC_VZ, REC_AR, REC_AG, REC_AB, REC_ROUGH, REC_PID, REC_XY, REC_DRAWS, REC_MODE,
+       REC_SX, REC_SY, REC_SZ, REC_WORDS };
+enum { MODE_DEAD = 0, MODE_FINAL = 1, MODE_DIFFUSE = 2, MODE_DIFFUSE_UNIT = 3, MODE_METAL = 4 };
+
 __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Queues q, int cur, int last_bounce)
 {
+    __shared__ float s_rec[4][REC_WORDS][kShadeRays];           // [warp][field][slot]: conflict-free for slot = lane + 32 g
+    __shared__ uint8_t s_req[4][kShadeRays];                    // slots that wait for a unit-sphere sample, in ray order
     const uint32_t count = q.counters[cur];
     const int nxt = cur ^ 1;
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    // whole warps iterate together so the ballot below is well defined
-    const uint32_t rounded = (count + 31u) & ~31u;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float (*rec)[kShadeRays] = s_rec[warp];
+    uint8_t* req = s_req[warp];
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     uint64_t local_rays = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-        bool alive = false;
-        float4 no, nd, nt;
-        if (i < count) {
-            const float4 o4 = q.ray_o[cur][i];
-            const uint32_t pid = __float_as_uint(o4.w);
-            if (pid != kInvalidPid) {
-                local_rays++;
-                const float4 d4 = q.ray_d[cur][i];
-                const float4 a4 = q.thr[cur][i];
-                const uint2 h = q.hit[i];
-                const f3 rayo = xyz(o4), raydir = xyz(d4);
-                f3 atten = xyz(a4);
-                const float t = __uint_as_float(h.x);
-                const int prim = (int)h.y;
-                if (!(prim >= 0 && t > 0.0f)) {
-                    const f3 c = atten * environment(sc, fp, raydir) * mk3(fp.bg_intensity);
-                    q.contrib[pid] = make_float4(c.x, c.y, c.z, 0.f);
-                } else {
-                    const ShadeRec* rec = sc.recs + prim;
-                    const float4 r0 = __ldg(&rec->r[0]), r1 = __ldg(&rec->r[1]), r2 = __ldg(&rec->r[2]);
-                    const uint32_t flags = __float_as_uint(r0.w);
-                    const int mat = __float_as_int(r2.y), texnum = __float_as_int(r2.z), rtexnum = __float_as_int(r2.w);
-                    const f3 hitpoint = rayo + mk3(t) * raydir;
-                    f3 N; f3 texco = mk3(0.f);
-                    if (flags & DRB_SF_SPHERE) {
-                        const float4 pa = __ldg(&sc.prims[prim].a), pb = __ldg(&sc.prims[prim].b);
-                        N = (hitpoint - xyz(pa)) / mk3(pb.x);                // kernel.cu:708, not normalised
-                    } else {
-                        // getnormal, kernel.cu:713-767
-                        if ((flags & DRB_SF_NEEDS_UV) || !(flags & DRB_SF_FACE_NORMAL)) {
-                            const float4 pa = __ldg(&sc.prims[prim].a), pb = __ldg(&sc.prims[prim].b), pc = __ldg(&sc.prims[prim].c);
-                            const f3 v0 = xyz(pa), e1 = xyz(pb), e2 = xyz(pc);
-                            N = cross(e1, e2);
-                            if (flags & DRB_SF_NEEDS_UV) {
-                                const f3 pvec = cross(raydir, e2);
-                                const float det = dot(e1, pvec);
-                                const float inv_det = 1.0f / det;
-                                const f3 tvec = rayo - v0;
-                                const float bu = dot(tvec, pvec) * inv_det;
-                                const f3 qvec = cross(tvec, e1);
-                                const float bv = dot(raydir, qvec) * inv_det;
-                                const float bw = 1.0f - bu - bv;
-                                const float4 r3 = __ldg(&rec->r[3]), r4 = __ldg(&rec->r[4]), r5 = __ldg(&rec->r[5]), r6 = __ldg(&rec->r[6]);
-                                texco = mk3(bw) * mk3(r3.w, r6.x, 0.f) + mk3(bu) * mk3(r4.w, r6.y, 0.f) + mk3(bv) * mk3(r5.w, r6.z, 0.f);
-                                if (flags & DRB_SF_SMOOTH) N = mk3(bw) * xyz(r3) + mk3(bu) * xyz(r4) + mk3(bv) * xyz(r5);
-                                else if (flags & DRB_SF_FACE_NORMAL) N = xyz(r0);
-                            }
-                        } else {
-                            N = xyz(r0);
-                        }
-                        N = normalize(N);
-                    }
-                    const bool front = dot(raydir, N) < 0.0f;                  // get_face_normal, kernel.cu:235-238
-                    if (!front) N = N * mk3(-1.0f);
-
-                    f3 ocolor = xyz(r1);
-                    float rough = r1.w;
-                    if (texnum >= 0) {
-                        const uchar4 c = tex_fetch(sc.textures, sc.ntextures, texnum, texco.x, -texco.y + 1.0f);
-                        ocolor = mk3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f);
-                    } else if (flags & DRB_SF_CHECKER) {
-                        // checker, kernel.cu:776-784
-                        const float yes = floorf(texco.x * 10.0f) + floorf(texco.y * 10.0f);
-                        if (fmodf(yes, 2.0f) == 0.0f) ocolor = mk3(0.8f);
-                    }
-                    if (rtexnum >= 0) {
-                        const uchar4 c = tex_fetch(sc.textures, sc.ntextures, rtexnum, texco.x, -texco.y + 1.0f);
-                        rough = (float)c.x / 255.0f / 2.0f;
-                    }
-
-                    const uint32_t xy = __float_as_uint(a4.w);
-                    const uint32_t smp = (pid >> 5) % fp.samples;              // slot = ((tile * samples) + s) * 32 + lane
-                    PathRng rng;
-                    rng.init(fp.seed, xy & 0xFFFFu, xy >> 16, fp.sample_base + smp, __float_as_uint(d4.w));
-
-                    f3 ndir = raydir;
-                    alive = true;
-                    // Every lobe that needs a point in the unit sphere draws it here, at one call site, so that the
-                    // diffuse, metal and glossy lanes of a warp run their rejection loops together.  Draw order per
-                    // path is the reference's: glossy picks its lobe first (kernel.cu:885), then samples.
-                    const float pick = mat == 5 ? rng.uniform() : 0.0f;
-                    const bool metal_lobe = mat == 3 || (mat == 5 && pick > 0.8f);
-                    const bool diffuse_lobe = mat == 0 || (mat == 5 && !(pick > 0.8f));
-                    f3 rs = mk3(0.f);
-                    if (metal_lobe || diffuse_lobe) rs = random_in_unit_sphere(rng);
-                    if (diffuse_lobe) {
-                        // diffuse, kernel.cu:848-866; the diffuse lobe of glossy (:900-910) never normalises the sample
-                        f3 target = hitpoint + N;
-                        if (mat == 5 || r2.x == 0.0f) target = target + rs;
-                        else target = target + normalize(rs);
-                        atten = atten * ocolor;
-                        ndir = normalize(target - hitpoint);
-                    } else if (metal_lobe) {
-                        const f3 reflected = reflect(normalize(raydir), N);     // metal, kernel.cu:875-883; glossy :886-898
-                        atten = atten * ocolor;
-                        ndir = reflected + mk3(rough) * rs;
-                    } else if (mat == 2) {
-                        atten = atten * ocolor;                                 // mirror, kernel.cu:867-874
-                        ndir = reflect(normalize(raydir), N);
-                    } else if (mat == 4) {
-                        // glass, kernel.cu:914-939 (ior comes from addional.y even when a roughness map is bound)
-                        const float ir = r1.w;
-                        const float ratio = front ? (float)(1.0 / (double)ir) : ir;
-                        const f3 unit = normalize(raydir);
-                        const float cos_theta = fminf(dot(unit * mk3(-1.0f), N), 1.0f);
-                        const float sin_theta = (float)sqrt(1.0 - (double)(cos_theta * cos_theta));
-                        const bool cannot_refract = (ratio * sin_theta) > 1.0f;
-                        if (cannot_refract || reflectance(cos_theta, ratio) > rng.uniform()) ndir = reflect(unit, N);
-                        else ndir = refract(unit, N, ratio);
-                        atten = atten * ocolor;
-                    } else {
-                        const f3 c = ocolor * atten;                            // emissive, kernel.cu:941-944
+    for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + warp) * (uint32_t)kShadeRays; base < count; base += warps_total * (uint32_t)kShadeRays) {
+        // ---- stage 1 ----------------------------------------------------------------------------------------------------
+        int nreq = 0, nalive = 0;
+#pragma unroll 1
+        for (int g = 0; g < kShadeGroups; ++g) {
+            const uint32_t i = base + (uint32_t)g * 32u + lane;
+            const int slot = g * 32 + (int)lane;
+            int mode = MODE_DEAD;
+            if (i < count) {
+                const float4 o4 = q.ray_o[cur][i];
+                const uint32_t pid = __float_as_uint(o4.w);
+                if (pid != kInvalidPid) {
+                    local_rays++;
+                    const float4 d4 = q.ray_d[cur][i];
+                    const float4 a4 = q.thr[cur][i];
+                    const uint2 h = q.hit[i];
+                    const f3 rayo = xyz(o4), raydir = xyz(d4);
+                    f3 atten = xyz(a4);
+                    const float t = __uint_as_float(h.x);
+                    const int prim = (int)h.y;
+                    if (!(prim >= 0 && t > 0.0f)) {
+                        const f3 c = atten * environment(sc, fp, raydir) * mk3(fp.bg_intensity);
                         q.contrib[pid] = make_float4(c.x, c.y, c.z, 0.f);
-                        alive = false;
-                    }
-                    if (alive && last_bounce) alive = false;                    // depth exhausted: black, kernel.cu:981
-                    if (alive) {
-                        no = make_float4(hitpoint.x, hitpoint.y, hitpoint.z, o4.w);
-                        nd = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(rng.draws));
-                        nt = make_float4(atten.x, atten.y, atten.z, a4.w);
+                    } else {
+                        const ShadeRec* srec = sc.recs + prim;
+                        const float4 r0 = __ldg(&srec->r[0]), r1 = __ldg(&srec->r[1]), r2 = __ldg(&srec->r[2]);
+                        const uint32_t flags = __float_as_uint(r0.w);
+                        const int mat = __float_as_int(r2.y), texnum = __float_as_int(r2.z), rtexnum = __float_as_int(r2.w);
+                        const f3 hitpoint = rayo + mk3(t) * raydir;
+                        f3 N; f3 texco = mk3(0.f);
+                        if (flags & DRB_SF_SPHERE) {
+                            const float4 pa = __ldg(&sc.prims[prim].a), pb = __ldg(&sc.prims[prim].b);
+                            N = (hitpoint - xyz(pa)) / mk3(pb.x);                // kernel.cu:708, not normalised
+                        } else {
+                            // getnormal, kernel.cu:713-767
+                            if ((flags & DRB_SF_NEEDS_UV) || !(flags & DRB_SF_FACE_NORMAL)) {
+                                const float4 pa = __ldg(&sc.prims[prim].a), pb = __ldg(&sc.prims[prim].b), pc = __ldg(&sc.prims[prim].c);
+                                const f3 v0 = xyz(pa), e1 = xyz(pb), e2 = xyz(pc);
+                                N = cross(e1, e2);
+                                if (flags & DRB_SF_NEEDS_UV) {
+                                    const f3 pvec = cross(raydir, e2);
+                                    const float det = dot(e1, pvec);
+                                    const float inv_det = 1.0f / det;
+                                    const f3 tvec = rayo - v0;
+                                    const float bu = dot(tvec, pvec) * inv_det;
+                                    const f3 qvec = cross(tvec, e1);
+                                    const float bv = dot(raydir, qvec) * inv_det;
+                                    const float bw = 1.0f - bu - bv;
+                                    const float4 r3 = __ldg(&srec->r[3]), r4 = __ldg(&srec->r[4]), r5 = __ldg(&srec->r[5]), r6 = __ldg(&srec->r[6]);
+                                    texco = mk3(bw) * mk3(r3.w, r6.x, 0.f) + mk3(bu) * mk3(r4.w, r6.y, 0.f) + mk3(bv) * mk3(r5.w, r6.z, 0.f);
+                                    if (flags & DRB_SF_SMOOTH) N = mk3(bw) * xyz(r3) + mk3(bu) * xyz(r4) + mk3(bv) * xyz(r5);
+                                    else if (flags & DRB_SF_FACE_NORMAL) N = xyz(r0);
+                                }
+                            } else {
+                                N = xyz(r0);
+                            }
+                            N = normalize(N);
+                        }
+                        const bool front = dot(raydir, N) < 0.0f;                  // get_face_normal, kernel.cu:235-238
+                        if (!front) N = N * mk3(-1.0f);
+
+                        f3 ocolor = xyz(r1);
+                        float rough = r1.w;
+                        if (texnum >= 0) {
+                            const uchar4 c = tex_fetch(sc.textures, sc.ntextures, texnum, texco.x, -texco.y + 1.0f);
+                            ocolor = mk3((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f);
+                        } else if (flags & DRB_SF_CHECKER) {
+                            // checker, kernel.cu:776-784
+                            const float yes = floorf(texco.x * 10.0f) + floorf(texco.y * 10.0f);
+                            if (fmodf(yes, 2.0f) == 0.0f) ocolor = mk3(0.8f);
+                        }
+                        if (rtexnum >= 0) {
+                            const uchar4 c = tex_fetch(sc.textures, sc.ntextures, rtexnum, texco.x, -texco.y + 1.0f);
+                            rough = (float)c.x / 255.0f / 2.0f;
+                        }
+                        if (!(mat == 0 || mat == 2 || mat == 3 || mat == 4 || mat == 5)) {
+                            const f3 c = ocolor * atten;                            // emissive, kernel.cu:941-944
+                            q.contrib[pid] = make_float4(c.x, c.y, c.z, 0.f);
+                        } else if (!last_bounce) {                                  // depth exhausted: black (kernel.cu:981), nothing to scatter
+                            uint32_t draws = __float_as_uint(d4.w);
+                            f3 vec;                                                 // successor direction (FINAL), normal (diffuse lobe) or mirror direction (metal lobe)
+                            atten = atten * ocolor;
+                            if (mat == 2) {
+                                vec = reflect(normalize(raydir), N);                // mirror, kernel.cu:867-874
+                                mode = MODE_FINAL;
+                            } else if (mat == 4) {
+                                // glass, kernel.cu:914-939 (ior comes from addional.y even when a roughness map is bound)
+                                const float ir = r1.w;
+                                const float ratio = front ? (float)(1.0 / (double)ir) : ir;
+                                const f3 unit = normalize(raydir);
+                                const float cos_theta = fminf(dot(unit * mk3(-1.0f), N), 1.0f);
+                                const float sin_theta = (float)sqrt(1.0 - (double)(cos_theta * cos_theta));
+                                bool mirror = (ratio * sin_theta) > 1.0f;
+                                if (!mirror) {
+                                    const uint32_t xy = __float_as_uint(a4.w);
+                                    PathRng rng;
+                                    rng.init(fp.seed, xy & 0xFFFFu, xy >> 16, fp.sample_base + (pid >> 5) % fp.samples, draws);
+                                    mirror = reflectance(cos_theta, ratio) > rng.uniform();
+                                    draws = rng.draws;
+                                }
+                                if (mirror) vec = reflect(unit, N); else vec = refract(unit, N, ratio);
+                                mode = MODE_FINAL;
+                            } else {
+                                bool metal_lobe = mat == 3;
+                                if (mat == 5) {                                     // glossy picks its lobe first, kernel.cu:885
+                                    const uint32_t xy = __float_as_uint(a4.w);
+                                    PathRng rng;
+                                    rng.init(fp.seed, xy & 0xFFFFu, xy >> 16, fp.sample_base + (pid >> 5) % fp.samples, draws);
+                                    metal_lobe = rng.uniform() > 0.8f;
+                                    draws = rng.draws;
+                                }
+                                if (metal_lobe) { vec = reflect(normalize(raydir), N); mode = MODE_METAL; }     // kernel.cu:875-883, 886-898
+                                else { vec = N; mode = (mat == 0 && r2.x != 0.0f) ? MODE_DIFFUSE_UNIT : MODE_DIFFUSE; }   // kernel.cu:848-866, 900-910
+                            }
+                            rec[REC_HX][slot] = hitpoint.x; rec[REC_HY][slot] = hitpoint.y; rec[REC_HZ][slot] = hitpoint.z;
+                            rec[REC_VX][slot] = vec.x; rec[REC_VY][slot] = vec.y; rec[REC_VZ][slot] = vec.z;
+                            rec[REC_AR][slot] = atten.x; rec[REC_AG][slot] = atten.y; rec[REC_AB][slot] = atten.z;
+                            rec[REC_ROUGH][slot] = rough;
+                            rec[REC_PID][slot] = o4.w; rec[REC_XY][slot] = a4.w;
+                            rec[REC_DRAWS][slot] = __uint_as_float(draws);
+                        }
                     }
                 }
             }
+            rec[REC_MODE][slot] = __int_as_float(mode);
+            nalive += __popc(__ballot_sync(0xffffffffu, mode != MODE_DEAD));
+            const unsigned mreq = __ballot_sync(0xffffffffu, mode >= MODE_DIFFUSE);
+            if (mode >= MODE_DIFFUSE) req[nreq + __popc(mreq & lt_mask)] = (uint8_t)slot;
+            nreq += __popc(mreq);
         }
-        // warp-aggregated append: one atomic per warp, order inside the warp preserved
-        const unsigned mask = __ballot_sync(0xffffffffu, alive);
-        if (mask) {
-            uint32_t base = 0;
-            if (lane == (unsigned)(__ffs(mask) - 1)) base = atomicAdd(&q.counters[nxt], (uint32_t)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-            if (alive) {
-                const uint32_t dst = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                q.ray_o[nxt][dst] = no;
-                q.ray_d[nxt][dst] = nd;
-                q.thr[nxt][dst] = nt;
+        if (nalive == 0) continue;                              // warp-uniform
+        __syncwarp();
+        // ---- stage 2: drain the request pool ------------------------------------------------------------------------------
+        if (nreq > 0) {
+            int next = 32;                                      // requests [0, 32) start on the lanes; the rest is handed out as lanes finish
+            int mine = -1;
+            uint32_t x = 0, y = 0, smp = 0, draws = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            bool regen = false;
+#define DRB_TAKE(r_) do { mine = (int)req[(r_)]; const uint32_t xy_ = __float_as_uint(rec[REC_XY][mine]), pid_ = __float_as_uint(rec[REC_PID][mine]); \
+                          x = xy_ & 0xFFFFu; y = xy_ >> 16; smp = fp.sample_base + (pid_ >> 5) % fp.samples; \
+                          draws = __float_as_uint(rec[REC_DRAWS][mine]); regen = (draws & 3u) != 0u; } while (0)
+            if ((int)lane < nreq) DRB_TAKE(lane);
+            for (;;) {
+                if (mine >= 0) {
+                    const uint32_t ph = draws & 3u;
+                    uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                    if (regen || ph != 1u) {                    // the block the stream resumes in, or the next one
+                        const Philox4 p = philox4x32_10((uint32_t)fp.seed, (uint32_t)(fp.seed >> 32), x, y, smp, regen ? (draws >> 2) : ((draws + 3u) >> 2));
+                        n0 = p.v[0]; n1 = p.v[1]; n2 = p.v[2]; n3 = p.v[3];
+                    }
+                    bool attempt = true;
+                    if (regen) { w0 = n0; w1 = n1; w2 = n2; w3 = n3; regen = false; attempt = (ph == 1u); }
+                    if (attempt) {
+                        // words draws, draws + 1, draws + 2 (PathRng::words3); the FIRST lands in the LAST component (see random_in_unit_sphere)
+                        const uint32_t wc = ph == 0u ? n0 : (ph == 1u ? w1 : (ph == 2u ? w2 : w3));
+                        const uint32_t wb = ph == 0u ? n1 : (ph == 1u ? w2 : (ph == 2u ? w3 : n0));
+                        const uint32_t wa = ph == 0u ? n2 : (ph == 1u ? w3 : (ph == 2u ? n0 : n1));
+                        if (ph != 1u) { w0 = n0; w1 = n1; w2 = n2; w3 = n3; }
+                        draws += 3u;
+                        const f3 p = mk3(PathRng::to_uniform(wa) * 2.0f - 1.0f, PathRng::to_uniform(wb) * 2.0f - 1.0f, PathRng::to_uniform(wc) * 2.0f - 1.0f);
+                        if (!(dot(p, p) >= 1.0f)) {
+                            rec[REC_SX][mine] = p.x; rec[REC_SY][mine] = p.y; rec[REC_SZ][mine] = p.z;
+                            rec[REC_DRAWS][mine] = __uint_as_float(draws);
+                            mine = -1;
+                        }
+                    }
+                }
+                const unsigned mfree = __ballot_sync(0xffffffffu, mine < 0);
+                if (next < nreq) {                              // warp-uniform
+                    if (mine < 0) {
+                        const int r = next + __popc(mfree & lt_mask);
+                        if (r < nreq) DRB_TAKE(r);
+                    }
+                    next += __popc(mfree);
+                } else if (mfree == 0xffffffffu) break;
             }
+#undef DRB_TAKE
+            __syncwarp();
         }
+        // ---- stage 3: finish and append in ray order ---------------------------------------------------------------------------
+        uint32_t dst0 = 0;
+        if (lane == 0) dst0 = atomicAdd(&q.counters[nxt], (uint32_t)nalive);
+        dst0 = __shfl_sync(0xffffffffu, dst0, 0);
+#pragma unroll 1
+        for (int g = 0; g < kShadeGroups; ++g) {
+            const int slot = g * 32 + (int)lane;
+            const int mode = __float_as_int(rec[REC_MODE][slot]);
+            const unsigned malive = __ballot_sync(0xffffffffu, mode != MODE_DEAD);
+            if (mode != MODE_DEAD) {
+                const f3 hp = mk3(rec[REC_HX][slot], rec[REC_HY][slot], rec[REC_HZ][slot]);
+                const f3 vec = mk3(rec[REC_VX][slot], rec[REC_VY][slot], rec[REC_VZ][slot]);
+                f3 ndir = vec;
+                if (mode >= MODE_DIFFUSE) {
+                    const f3 rs = mk3(rec[REC_SX][slot], rec[REC_SY][slot], rec[REC_SZ][slot]);
+                    if (mode == MODE_METAL) ndir = vec + mk3(rec[REC_ROUGH][slot]) * rs;
+                    else {
+                        f3 target = hp + vec;
+                        if (mode == MODE_DIFFUSE) target = target + rs; else target = target + normalize(rs);
+                        ndir = normalize(target - hp);
+                    }
+                }
+                const uint32_t dst = dst0 + (uint32_t)__popc(malive & lt_mask);
+                q.ray_o[nxt][dst] = make_float4(hp.x, hp.y, hp.z, rec[REC_PID][slot]);
+                q.ray_d[nxt][dst] = make_float4(ndir.x, ndir.y, ndir.z, rec[REC_DRAWS][slot]);
+                q.thr[nxt][dst] = make_float4(rec[REC_AR][slot], rec[REC_AG][slot], rec[REC_AB][slot], rec[REC_XY][slot]);
+            }
+            dst0 += (uint32_t)__popc(malive);
+        }
+        __syncwarp();                                           // the records are rewritten by the next iteration
     }
     // ray statistics: one 64-bit atomic per warp
 #pragma unroll
@@ -1011,7 +1107,7 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
             if (stats) { auto e0 = pool.get(), e1 = pool.get(); trace_ev.push_back({ e0, e1 }); DRB_CUDA(cudaEventRecord(e0, stream)); }
             k_trace<<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(sc, fp.scene_scale, q, cur, g_refill, g_leaf_batch, g_step_min, order);
             if (stats) DRB_CUDA(cudaEventRecord(trace_ev.back().second, stream));
-            k_shade<<<std::min<uint32_t>((uint32_t)rb->shade_blocks, (live + 127u) / 128u), 128, 0, stream>>>(sc, fp, q, cur, b == st->max_depth - 1 ? 1 : 0);
+            k_shade<<<std::min<uint32_t>((uint32_t)rb->shade_blocks, (live + 4u * kShadeRays - 1u) / (4u * kShadeRays)), 128, 0, stream>>>(sc, fp, q, cur, b == st->max_depth - 1 ? 1 : 0);
             k_prepare<<<1, 32, 0, stream>>>(q.counters, cur, -1, 0u);
             launches += 3; trace_launches += 1;
             cur ^= 1;

@@ -9,7 +9,8 @@
 //   63-bit Morton key of the box centre -> stable radix sort of (key, slot)
 //   Karras 2012 hierarchy over the sorted keys (ties broken by position)
 //   bottom-up refit with one atomic flag per internal node
-//   emit 32 B nodes that carry both child boxes, quantised to 16 bits on a scene-wide grid
+//   SAH-guided re-clustering of the sorted leaves, then a breadth-first collapse to 64 B four-wide nodes whose
+//   child boxes are quantised to 16 bits on a scene-wide grid (both loops inside cooperative kernels)
 // All floating-point steps that feed integer outputs (keys) use single IEEE operations (this TU is
 // compiled with -fmad=false), so oracle/lbvh_host.c reproduces keys, order and topology bit-exactly.
 #include "drb_internal.h"
