@@ -386,6 +386,8 @@ class Scene:
         """The object lines are already in device memory (hs.num_objects records of OBJECT_DTYPE at `objects_ptr`, e.g.
         all-gathered over NVLink from per-rank partial uploads); `stream` is the stream that produced them."""
         h = C.c_void_p()
+        if stream == 0:
+            stream = 1                                # cudaStreamLegacy, see Scene._opts
         _check(_lib.drb_scene_create_from_device(hs.handle, device, build_flags, objects_ptr, stream, C.byref(h)))
         return cls(h)
 
@@ -455,7 +457,10 @@ class Scene:
         if sample_count is not None:
             flags |= FLAG_EXACT_SAMPLES
         o.seed, o.sample_base, o.sample_count, o.batch_paths, o.flags = seed, sample_base, int(sample_count or 0), batch_paths, flags
-        o.stream = stream
+        # None -> the scene's own (non-blocking) stream.  0 is how torch names the legacy default stream
+        # (torch.cuda.current_stream().cuda_stream outside a stream context); the C ABI reads a NULL stream as "the scene's
+        # own", so the legacy default stream travels as its CUDA handle cudaStreamLegacy (0x1).
+        o.stream = None if stream is None else (1 if stream == 0 else stream)
         o.tile_rank, o.tile_count = tile_rank, tile_count
         return o
 

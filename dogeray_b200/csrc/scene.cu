@@ -1110,6 +1110,8 @@ int drb_scene_create_multi(const drb_host_scene* hs, const int* devices, int nde
         if (cudaHostRegister((void*)hs->objects.data(), nobj * sizeof(drb_object), cudaHostRegisterPortable) == cudaSuccess) hs->pinned = true;
         else cudaGetLastError();
     }
+    const bool debug = getenv("DOGERAY_B200_DEBUG") != nullptr;
+    auto trace = [&](const char* fmt, int a, int b) { if (debug) { fprintf(stderr, "[dogeray_b200] create_multi: "); fprintf(stderr, fmt, a, b); fputc('\n', stderr); fflush(stderr); } };
     // share k = object lines [k * chunk, (k + 1) * chunk): uploaded by device k, pulled by all the others
     const size_t chunk = (nobj + (size_t)ndevices - 1) / (size_t)ndevices;
     struct Side { drb_object* buf = nullptr; cudaStream_t st = nullptr; cudaEvent_t uploaded = nullptr, pulled = nullptr; int rc = DRB_OK; std::string err; };
@@ -1127,6 +1129,7 @@ int drb_scene_create_multi(const drb_host_scene* hs, const int* devices, int nde
         size_t lo, hi; share(k, &lo, &hi);
         if (hi > lo && cudaMemcpyAsync(sd.buf + lo, hs->objects.data() + lo, (hi - lo) * sizeof(drb_object), cudaMemcpyHostToDevice, sd.st) != cudaSuccess) { bad("upload"); break; }
         if (cudaEventRecord(sd.uploaded, sd.st) != cudaSuccess) { bad("cudaEventRecord"); break; }
+        trace("share %d uploading on device %d", k, devices[k]);
     }
     bool ok = true;
     for (const Side& sd : side) ok = ok && sd.rc == DRB_OK;
@@ -1144,24 +1147,30 @@ int drb_scene_create_multi(const drb_host_scene* hs, const int* devices, int nde
                 size_t lo, hi; share(j, &lo, &hi);
                 if (hi <= lo) continue;
                 if (cudaStreamWaitEvent(sd.st, side[(size_t)j].uploaded, 0) != cudaSuccess) return bad("cudaStreamWaitEvent");
-                if (cudaMemcpyPeerAsync(sd.buf + lo, devices[k], side[(size_t)j].buf + lo, devices[j], (hi - lo) * sizeof(drb_object), sd.st) != cudaSuccess) return bad("peer copy");
+                const cudaError_t ce = devices[j] == devices[k]
+                    ? cudaMemcpyAsync(sd.buf + lo, side[(size_t)j].buf + lo, (hi - lo) * sizeof(drb_object), cudaMemcpyDeviceToDevice, sd.st)
+                    : cudaMemcpyPeerAsync(sd.buf + lo, devices[k], side[(size_t)j].buf + lo, devices[j], (hi - lo) * sizeof(drb_object), sd.st);
+                if (ce != cudaSuccess) return bad("peer copy");
+                trace("pulled share %d into %d", j, k);
             }
             if (cudaEventRecord(sd.pulled, sd.st) != cudaSuccess) return bad("cudaEventRecord");
+            trace("building scene %d on device %d", k, devices[k]);
             sd.rc = drb_scene_create_from_device(hs, devices[k], build_flags, sd.buf, sd.st, &out[k]);
             if (sd.rc != DRB_OK) sd.err = drb_last_error();
+            trace("scene %d: rc %d", k, sd.rc);
         };
         std::vector<std::thread> pool;
         for (int k = 1; k < ndevices; ++k) pool.emplace_back(work, k);
         work(0);
         for (auto& th : pool) th.join();
     }
+    trace("threads joined (%d devices, ok %d)", ndevices, ok ? 1 : 0);
     // a share may be freed only after every device has pulled it
+    for (int k = 0; k < ndevices; ++k)
+        if (side[(size_t)k].st && cudaSetDevice(devices[k]) == cudaSuccess) cudaStreamSynchronize(side[(size_t)k].st);
     for (int k = 0; k < ndevices; ++k) {
         Side& sd = side[(size_t)k];
         if (cudaSetDevice(devices[k]) != cudaSuccess) { cudaGetLastError(); continue; }
-        for (int j = 0; j < ndevices; ++j)
-            if (side[(size_t)j].pulled) cudaEventSynchronize(side[(size_t)j].pulled);
-        if (sd.st) cudaStreamSynchronize(sd.st);
         if (sd.buf) drb_dev_free(sd.buf, sd.st);
         if (sd.uploaded) cudaEventDestroy(sd.uploaded);
         if (sd.pulled) cudaEventDestroy(sd.pulled);

@@ -184,7 +184,8 @@ typedef struct drb_opts {
     uint32_t sample_count;      /* samples per pixel to trace in this call; 0 -> settings->spp, unless DRB_FLAG_EXACT_SAMPLES */
     uint32_t batch_paths;       /* paths in flight per wavefront batch; 0 -> 128 M (15 GB of queues), at most 1/4 of device memory */
     uint32_t flags;             /* DRB_FLAG_* */
-    void* stream;               /* cudaStream_t to launch on; NULL -> the scene's own stream */
+    void* stream;               /* cudaStream_t to launch on; NULL -> the scene's own (non-blocking) stream.  For the legacy
+                                 * default stream pass cudaStreamLegacy, not 0 */
     uint32_t tile_rank;         /* tile sharding: trace only the 8x4-pixel tiles t with t % tile_count == tile_rank;  */
     uint32_t tile_count;        /* pixels of other tiles are left untouched in accum.  0 or 1 -> the whole image      */
 } drb_opts;

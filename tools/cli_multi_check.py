@@ -25,11 +25,13 @@ cli = os.path.join(os.path.dirname(drb.__file__), "dogeray-b200")
 d = tempfile.mkdtemp(prefix="drb_cli_")
 objs, st = synth.city_scene() if which == "city10m" else synth.instanced_grid_scene()
 res = "%dx%d" % (st.width, st.height)
-drb.write_rts(os.path.join(d, "scene.rts"), st, objs)
 ndev = drb.device_count()
 out, rows = {}, []
+use_cli = which != "city10m"            # the 10 M-triangle scene is 3.3 GB of text: it goes through the library only
+if use_cli:
+    drb.write_rts(os.path.join(d, "scene.rts"), st, objs)
 for n in (1, 2, 4, 8):
-    if n > ndev:
+    if n > ndev or not use_cli:
         continue
     for mode, extra in (("tiles", []), ("dynamic", ["--dynamic"]), ("samples", ["--shard", "samples"])):
         if n == 1 and mode != "tiles":
@@ -49,19 +51,29 @@ for n in (1, 2, 4, 8):
         if mode != "samples":
             assert out[(n, mode)] == out[(1, "tiles")], "image differs from the 1-GPU image"
 # static imbalance through the library
-hs = drb.HostScene.load(os.path.join(d, "scene.rts"), d, cache=True)
-for n in (2, 4, 8):
+hs = drb.HostScene.load(os.path.join(d, "scene.rts"), d, cache=True) if use_cli else drb.HostScene.from_objects(objs, st)
+one = None
+for n in (1, 2, 4, 8):
     if n > ndev:
         continue
+    t0 = time.time()
     scenes = drb.create_multi(hs, list(range(n)))
+    t_create = time.time() - t0
     s1 = st.replace(spp=int(spp))
     drb.render_multi(scenes, s1, seed=0)                             # warm-up (buffers)
-    _, sm = drb.render_multi(scenes, s1, seed=0)
+    t0 = time.time()
+    img, sm = drb.render_multi(scenes, s1, seed=0)
+    wall = time.time() - t0
     times = drb.render_multi_times()
-    _, sd = drb.render_multi(scenes, s1, seed=0, dynamic=True)
+    if n == 1:
+        one = img
+    imgd, sd = drb.render_multi(scenes, s1, seed=0, dynamic=True)
     dtimes = drb.render_multi_times()
-    print(json.dumps({"scene": which, "gpus": n, "static_ms_per_handle": [round(t, 2) for t in times], "static_imbalance": max(times) / (sum(times) / n) - 1,
-                      "static_frame_ms": max(times), "dynamic_busy_ms_per_handle": [round(t, 2) for t in dtimes], "dynamic_frame_ms": max(dtimes)}), flush=True)
+    print(json.dumps({"scene": which, "res": res, "spp": int(spp), "gpus": n, "create_multi_s": round(t_create, 3), "render_multi_wall_ms": round(wall * 1e3, 2),
+                      "mrays_s_wall": round(sm.rays / wall / 1e6, 1), "static_ms_per_handle": [round(t, 2) for t in times],
+                      "static_imbalance": max(times) / (sum(times) / n) - 1, "static_frame_ms": max(times),
+                      "dynamic_busy_ms_per_handle": [round(t, 2) for t in dtimes], "dynamic_frame_ms": max(dtimes),
+                      "bit_identical_to_1gpu": bool(np.array_equal(img, one)) and bool(np.array_equal(imgd, one))}), flush=True)
     for sc in scenes:
         sc.close()
 print("done")
