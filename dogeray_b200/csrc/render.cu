@@ -548,7 +548,9 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Q
                         if (!(mat == 0 || mat == 2 || mat == 3 || mat == 4 || mat == 5)) {
                             const f3 c = ocolor * atten;                            // emissive, kernel.cu:941-944
                             q.contrib[pid] = make_float4(c.x, c.y, c.z, 0.f);
-                        } else if (!last_bounce) {                                  // depth exhausted: black (kernel.cu:981), nothing to scatter
+                        } else if (last_bounce) {
+                            q.contrib[pid] = make_float4(0.f, 0.f, 0.f, 0.f);       // depth exhausted: black (kernel.cu:981), nothing to scatter
+                        } else {
                             uint32_t draws = __float_as_uint(d4.w);
                             f3 vec;                                                 // successor direction (FINAL), normal (diffuse lobe) or mirror direction (metal lobe)
                             atten = atten * ocolor;
@@ -1079,7 +1081,9 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
         fp.samples = std::min(per_batch, total_samples - done);
         fp.sample_base = o.sample_base + done;
         const uint32_t nslots = (uint32_t)(slots_per_sample * fp.samples);
-        DRB_CUDA(cudaMemsetAsync(q.contrib, 0, (size_t)nslots * sizeof(float4), stream));
+        // no clearing of contrib[]: every path ends exactly once (miss, emissive hit, or black at the depth limit) and
+        // writes its slot then; slots of pixels outside the image are never read.  (No bounce at all: everything is black.)
+        if (st->max_depth == 0) DRB_CUDA(cudaMemsetAsync(q.contrib, 0, (size_t)nslots * sizeof(float4), stream));
         k_generate<<<(nslots + 255) / 256, 256, 0, stream>>>(fp, nslots, q);
         k_prepare<<<1, 32, 0, stream>>>(q.counters, 1, 0, nslots);
         launches += 2;

@@ -332,6 +332,12 @@ def test_zero_samples_means_zero_samples():
     assert sn.paths == 0 and sn.rays == 0 and not none.any()
     kept, _ = sc.render(st, seed=9, sample_count=0, accumulate_into=full.copy())
     assert np.array_equal(kept, full)
+    # no bounce at all: raycolor's loop never runs and returns black (kernel.cu:793, 981); twice, so stale buffers would show
+    for _ in range(2):
+        black, sb = sc.render(st.replace(max_depth=0), seed=9)
+        assert sb.rays == 0 and not black.any()
+    one, s1 = sc.render(st.replace(max_depth=1), seed=9)                     # only misses shine at depth 1
+    assert s1.rays == 40 * 24 * 3 and one.max() > 0
     # spp < ranks: the shares of 8 ranks, summed, are the 3-sample frame
     from dogeray_b200.distributed import shard_samples
     acc = np.zeros_like(full)
