@@ -1026,21 +1026,26 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
     const size_t tiles_total = (size_t)tiles_x * tiles_y;
     const size_t my_tiles = tiles_total > tile_rank ? (tiles_total - tile_rank + tile_count - 1) / tile_count : 0;
     const size_t slots_per_sample = std::max<size_t>(my_tiles, 1) * 32;
-    // Paths in flight per wavefront batch.  The last bounces of a batch hold few rays and run at the latency floor,
-    // so bigger batches amortise them (1080p, 1 M triangles: 16 M paths 509 ms per frame, 128 M paths 465 ms).  A path
-    // slot costs 120 B of queues; by default take 128 M slots (15 GB) but never more than a quarter of the device memory,
-    // and halve on allocation failure.
+    // Paths in flight per wavefront batch.  The last bounces of a batch hold few rays and run at the latency floor, and
+    // every launch has a tail, so bigger batches amortise both (1080p, 256 spp, 1 M triangles: 16 M paths per batch 509 ms
+    // per frame, 128 M 424 ms, 531 M -- the whole frame in one batch -- 417 ms).  A path slot costs 120 B of queues; by
+    // default a batch may take 40 % of the device memory (B200: 73 GB, 610 M slots).  The samples are then cut into
+    // EQUAL batches (no small last one), and the batch is halved on allocation failure.
     size_t want = o.batch_paths;
     if (!want) {
         want = (size_t)128 << 20;
         const size_t device_mem = device_total_mem(s->device);
-        if (device_mem) want = std::max<size_t>(std::min(want, (size_t)(0.25 * (double)device_mem) / 120), (size_t)1 << 20);
+        if (device_mem) want = std::max<size_t>((size_t)(0.40 * (double)device_mem) / 120, (size_t)1 << 20);
     }
     uint32_t per_batch = 1;
     for (;;) {
         per_batch = (uint32_t)std::max<size_t>(1, want / slots_per_sample);
         per_batch = std::min<uint32_t>(per_batch, std::max<uint32_t>(total_samples, 1u));
         if (slots_per_sample * per_batch >= 0xFFFFFFF0ull) { want /= 2; continue; }
+        if (total_samples > per_batch) {
+            const uint32_t nbatches = (total_samples + per_batch - 1) / per_batch;
+            per_batch = (total_samples + nbatches - 1) / nbatches;
+        }
         const int rc = ensure_buffers(s, slots_per_sample * per_batch);
         if (rc == DRB_OK) break;
         if (per_batch == 1) return rc;                  // not even one sample per pixel fits

@@ -182,7 +182,7 @@ typedef struct drb_opts {
     uint64_t seed;              /* Philox key */
     uint32_t sample_base;       /* first sample index of this call */
     uint32_t sample_count;      /* samples per pixel to trace in this call; 0 -> settings->spp, unless DRB_FLAG_EXACT_SAMPLES */
-    uint32_t batch_paths;       /* paths in flight per wavefront batch; 0 -> 128 M (15 GB of queues), at most 1/4 of device memory */
+    uint32_t batch_paths;       /* paths in flight per wavefront batch (120 B of queues each); 0 -> up to 40 % of device memory */
     uint32_t flags;             /* DRB_FLAG_* */
     void* stream;               /* cudaStream_t to launch on; NULL -> the scene's own (non-blocking) stream.  For the legacy
                                  * default stream pass cudaStreamLegacy, not 0 */
