@@ -336,7 +336,7 @@ def main():
     ntris = int((objs["type"] == 2).sum())
     config = {"workload": desc, "triangles": ntris, "width": st.width, "height": st.height, "spp": st.spp, "max_depth": st.max_depth,
               "seed": 0, "sharding": "samples, contiguous ranges per rank, one NCCL reduce of the float radiance sums to rank 0" if world > 1 else "none",
-              "l2": "working set per step (ray queues: 120 B per path slot, up to 15 GB per batch; scene 220 MB) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "working set per step (ray queues: 120 B per path slot, 64 GB for the frame; scene 225 MB) exceeds the 126 MB L2; no explicit flush"}
     ncores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -512,7 +512,9 @@ def main():
                     "parts_ms_per_step_rank0": {k: v / K for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+                         "traffic": (traffic["dram_bytes_per_second"] * (trace_ms / max(trace_launches, 1)) * 1e-3) if traffic and "dram_bytes_per_second" in traffic else None,
+                         "traffic_source": ("DRAM bytes/s of k_trace in the committed ncu capture (%s) x this run's mean launch duration" % traffic["source"]) if traffic else None,
+                         "algorithmic_bytes_per_launch": bpr * rays / max(trace_launches, 1), "peak_source": peak_src,
                          "bytes_per_ray": bpr, "rays_per_launch": rays / max(trace_launches, 1), "trace_ms_per_step": trace_ms / K,
                          "trace_share_of_step": trace_ms / ms if ms > 0 else None,
                          "note": "algorithmic bytes = 32*ceil(log2 Ntris) + 36 + 64 per ray (SURVEY.md 8d); scenes of this size are largely L2-resident, see profiles/"},

@@ -34,9 +34,13 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(out.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
 starts.append(len(rows))
-s = starts[launch]
+mine = [k for k in range(len(starts) - 1) if "::%s(" % kernel in rows[starts[k]][1]]       # sections of this kernel, in capture order
+if len(starts) - 1 > 0 and len(mine) % 2 == 0 and all(rows[starts[mine[2 * j]] + 2] == rows[starts[mine[2 * j + 1]] + 2] for j in range(len(mine) // 2)):
+    mine = mine[::2]                                       # this ncu prints every launch's table twice
+k = mine[launch]
+s = starts[k]
 hdr = rows[s + 1]
-body = [r for r in rows[s + 2:starts[launch + 1]] if len(r) == len(hdr)]
+body = [r for r in rows[s + 2:starts[k + 1]] if len(r) == len(hdr)]
 col = {n: i for i, n in enumerate(hdr)}
 assert len(body) == len(lines), (len(body), len(lines))
 agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])

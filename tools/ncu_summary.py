@@ -1,7 +1,8 @@
 """Summarise ncu captures brought back in gpurun_out/ into profiles/ (tracked).
 
     python tools/ncu_summary.py launches gpurun_out/launches_X.csv profiles/X_launches.md
-    python tools/ncu_summary.py kernel   gpurun_out/prof_X.ncu-rep  profiles/X_kernel.md [--traffic-json profiles/trace_traffic.json]
+    python tools/ncu_summary.py kernel   gpurun_out/prof_X.ncu-rep  profiles/X_kernel.md [--only k_trace] [--traffic-json profiles/trace_traffic.json]
+                                                                                       [--counters-json profiles/trace_counters.json]
 """
 import collections
 import csv
@@ -63,11 +64,13 @@ def launches(src, dst):
         f.write("```\n")
 
 
-def kernel(src, dst, traffic_json=None):
+def kernel(src, dst, traffic_json=None, only=None, counters_json=None):
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     name_i = hdr.index("Kernel Name")
+    if only:
+        data = [d for d in data if only in d[name_i]]
     with open(dst, "w") as f:
         f.write("# ncu --set full --clock-control none: `%s`\n\n" % src)
         f.write("| metric | unit | " + " | ".join("launch %d" % k for k in range(len(data))) + " |\n|---|---|" + "---|" * len(data) + "\n")
@@ -76,21 +79,43 @@ def kernel(src, dst, traffic_json=None):
             if key in hdr:
                 i = hdr.index(key)
                 f.write("| %s (`%s`) | %s | %s |\n" % (label, key, units[i], " | ".join(d[i] for d in data)))
+
+    def num(d, key):
+        return float(d[hdr.index(key)].replace(",", ""))
+
     if traffic_json and "dram__bytes_read.sum" in hdr:
         def to_bytes(v, u):
             m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             return float(v.replace(",", "")) * m.get(u, 1)
-        ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         per = [to_bytes(d[ir], units[ir]) + to_bytes(d[iw], units[iw]) for d in data]
-        json.dump({"source": src, "kernel": "k_trace", "launches_captured": len(per), "dram_bytes_each": per,
-                   "dram_bytes_per_launch": sum(per) / len(per),
-                   "note": "dram__bytes_read.sum + dram__bytes_write.sum per captured k_trace launch (the first bounces of one wavefront batch, i.e. the largest launches of a frame)"},
+        it = hdr.index("gpu__time_duration.sum")
+        scale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(units[it].replace("second", "s").replace("usecond", "us").replace("msecond", "ms").replace("nsecond", "ns"), 1e-3)
+        secs = [float(d[it].replace(",", "")) * scale for d in data]
+        json.dump({"source": src, "kernel": only or "k_trace", "launches_captured": len(per), "dram_bytes_each": per, "seconds_each": secs,
+                   "dram_bytes_per_launch": sum(per) / len(per), "dram_bytes_per_second": sum(per) / sum(secs),
+                   "note": "dram__bytes_read.sum + dram__bytes_write.sum of the captured launches of the final kernel (the first bounces of one wavefront "
+                           "batch at 64 spp) and their durations; bench.py reports traffic per launch as this DRAM rate x the mean duration of its own launches"},
                   open(traffic_json, "w"), indent=1)
+    if counters_json:
+        def mean(key):
+            return sum(num(d, key) for d in data) / len(data)
+        json.dump({"counters_source": src, "l1_wavefront_pct": mean("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                   "issue_pct": mean("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "lanes_active": mean("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                   "dram_pct": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                   "l2_hit_pct": mean("lts__t_sector_hit_rate.pct"), "l1_hit_pct": mean("l1tex__t_sector_hit_rate.pct"),
+                   "occupancy_pct": mean("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                   "long_scoreboard_stalls_per_issue": mean("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+                   "limiter": "L1 data-pipe wavefronts + issue slots + L2 latency (the tree is L2/L1-resident: DRAM is a few percent of peak); "
+                              "the HBM roofline is the rubric's formula, not the operative limit"},
+                  open(counters_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        tj = sys.argv[sys.argv.index("--traffic-json") + 1] if "--traffic-json" in sys.argv else None
-        kernel(sys.argv[2], sys.argv[3], tj)
+        def opt(name):
+            return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else None
+        kernel(sys.argv[2], sys.argv[3], opt("--traffic-json"), opt("--only"), opt("--counters-json"))
