@@ -444,7 +444,8 @@ DRB_D f3 environment(const DevScene& sc, const FrameParams& fp, f3 raydir)
 //      leaves a record: its finished successor (mirror, glass), or what stage 3 needs plus a sampling request;
 //   2  the requests form a pool that the 32 lanes drain with per-lane refill: a lane makes one attempt per iteration and
 //      takes the next request as soon as its own is accepted, so the lanes stay busy until the pool is dry.  ONE Philox
-//      call site serves the block a stream resumes in and the blocks after it;
+//      call site serves the block a stream resumes in and the blocks after it.  The last few requests are finished by
+//      TEAMS of lanes that try consecutive attempts of one stream side by side;
 //   3  (full width) finishes the scatter from record + sample and appends the successors IN RAY ORDER with one atomic
 //      for the whole group -- the next bounce sees the same queue order as a ray-per-lane pass would give it.
 // Every path consumes exactly the words it always did (draw n of a path is word n of its Philox stream), so the image
@@ -454,6 +455,10 @@ DRB_D f3 environment(const DevScene& sc, const FrameParams& fp, f3 raydir)
 #endif
 constexpr int kShadeGroups = DRB_SHADE_GROUPS;          // 32-ray groups per warp iteration
 constexpr int kShadeRays = 32 * kShadeGroups;
+#ifndef DRB_SHADE_TEAM_AT
+#define DRB_SHADE_TEAM_AT 8
+#endif
+constexpr int kShadeTeamAt = DRB_SHADE_TEAM_AT;          // open requests from which the sampling pool is finished in teams
 enum { REC_HX = 0, REC_HY, REC_HZ, REC_VX, REC_VY, REC_VZ, REC_AR, REC_AG, REC_AB, REC_ROUGH, REC_PID, REC_XY, REC_DRAWS, REC_MODE,
        REC_SX, REC_SY, REC_SZ, REC_WORDS };
 enum { MODE_DEAD = 0, MODE_FINAL = 1, MODE_DIFFUSE = 2, MODE_DIFFUSE_UNIT = 3, MODE_METAL = 4 };
@@ -646,9 +651,55 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Q
                         if (r < nreq) DRB_TAKE(r);
                     }
                     next += __popc(mfree);
-                } else if (mfree == 0xffffffffu) break;
+                } else if (__popc(~mfree) <= kShadeTeamAt) break;   // the pool is dry and few requests are left: finish them in teams
             }
 #undef DRB_TAKE
+            // The tail.  The last requests would run alone for several more attempts; instead every one of them gets a
+            // TEAM of lanes: helper h of a team generates block (draws >> 2) + h of the request's stream, borrows the first
+            // two words of its right neighbour's block, and tries every attempt that STARTS in its block (attempt a starts at
+            // word draws + 3 a).  The attempts of a team cover the stream in order, so the first accepting helper holds
+            // exactly the sample the one-lane loop would have found, and writes it.
+            unsigned act = __ballot_sync(0xffffffffu, mine >= 0);
+            while (act) {
+                const int u = __popc(act);
+                const int tshift = u > 4 ? 2 : (u > 2 ? 3 : (u > 1 ? 4 : 5));          // team size 4, 8, 16 or 32 lanes
+                const int tsize = 1 << tshift;
+                const int j = (int)lane >> tshift, h = (int)lane & (tsize - 1);
+                const bool serving = j < u;
+                const int owner = (int)__fns(act, 0u, (serving ? j : 0) + 1);             // the j-th open request sits on this lane
+                const uint32_t ox = __shfl_sync(0xffffffffu, x, owner), oy = __shfl_sync(0xffffffffu, y, owner);
+                const uint32_t os = __shfl_sync(0xffffffffu, smp, owner), od = __shfl_sync(0xffffffffu, draws, owner);
+                const int oslot = __shfl_sync(0xffffffffu, mine, owner);
+                const uint32_t blk = (od >> 2) + (uint32_t)h;
+                const Philox4 pb = philox4x32_10((uint32_t)fp.seed, (uint32_t)(fp.seed >> 32), ox, oy, os, blk);
+                const uint32_t m0 = __shfl_down_sync(0xffffffffu, pb.v[0], 1), m1 = __shfl_down_sync(0xffffffffu, pb.v[1], 1);
+                const bool has_next = h + 1 < tsize;
+                const uint32_t base = blk << 2;
+                uint32_t first;                                                             // offset in my block of the first attempt starting there
+                if (h == 0) first = od & 3u; else { const uint32_t r = (base - od) % 3u; first = r ? 3u - r : 0u; }
+                const uint32_t a0 = first == 0u ? pb.v[0] : (first == 1u ? pb.v[1] : (first == 2u ? pb.v[2] : pb.v[3]));
+                const uint32_t a1 = first == 0u ? pb.v[1] : (first == 1u ? pb.v[2] : (first == 2u ? pb.v[3] : m0));
+                const uint32_t a2 = first == 0u ? pb.v[2] : (first == 1u ? pb.v[3] : (first == 2u ? m0 : m1));
+                const f3 pa = mk3(PathRng::to_uniform(a2) * 2.0f - 1.0f, PathRng::to_uniform(a1) * 2.0f - 1.0f, PathRng::to_uniform(a0) * 2.0f - 1.0f);
+                const bool acc_a = serving && (first < 2u || has_next) && !(dot(pa, pa) >= 1.0f);
+                // a second attempt starts at word 3 of my block when the first one started at word 0
+                const f3 pc = mk3(PathRng::to_uniform(m1) * 2.0f - 1.0f, PathRng::to_uniform(m0) * 2.0f - 1.0f, PathRng::to_uniform(pb.v[3]) * 2.0f - 1.0f);
+                const bool acc_c = serving && first == 0u && has_next && !(dot(pc, pc) >= 1.0f);
+                const unsigned macc = __ballot_sync(0xffffffffu, acc_a || acc_c);
+                const unsigned team = tsize == 32 ? 0xffffffffu : (((1u << tsize) - 1u) << (j << tshift));
+                if ((acc_a || acc_c) && (macc & team & lt_mask) == 0u) {                    // the first accepting helper of its team
+                    const f3 pw = acc_a ? pa : pc;
+                    rec[REC_SX][oslot] = pw.x; rec[REC_SY][oslot] = pw.y; rec[REC_SZ][oslot] = pw.z;
+                    rec[REC_DRAWS][oslot] = __uint_as_float(base + (acc_a ? first : 3u) + 3u);
+                }
+                if (mine >= 0) {
+                    const int myj = __popc(act & lt_mask);
+                    const unsigned myteam = tsize == 32 ? 0xffffffffu : (((1u << tsize) - 1u) << (myj << tshift));
+                    if (macc & myteam) mine = -1;
+                    else draws += 3u * (((uint32_t)(4 << tshift) - (draws & 3u)) / 3u);     // every attempt inside the team's blocks was rejected
+                }
+                act = __ballot_sync(0xffffffffu, mine >= 0);
+            }
             __syncwarp();
         }
         // ---- stage 3: finish and append in ray order ---------------------------------------------------------------------------
