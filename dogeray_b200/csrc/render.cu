@@ -463,7 +463,10 @@ enum { REC_HX = 0, REC_HY, REC_HZ, REC_VX, REC_VY, REC_VZ, REC_AR, REC_AG, REC_A
        REC_SX, REC_SY, REC_SZ, REC_WORDS };
 enum { MODE_DEAD = 0, MODE_FINAL = 1, MODE_DIFFUSE = 2, MODE_DIFFUSE_UNIT = 3, MODE_METAL = 4 };
 
-__global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, FrameParams fp, Queues q, int cur, int last_bounce)
+#ifndef DRB_SHADE_MIN_BLOCKS
+#define DRB_SHADE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, DRB_SHADE_MIN_BLOCKS) k_shade(DevScene sc, FrameParams fp, Queues q, int cur, int last_bounce)
 {
     __shared__ float s_rec[4][REC_WORDS][kShadeRays];           // [warp][field][slot]: conflict-free for slot = lane + 32 g
     __shared__ uint8_t s_req[4][kShadeRays];                    // slots that wait for a unit-sphere sample, in ray order

@@ -46,4 +46,5 @@ def test_gpu_arm_line():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "traffic" in r
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert d["parity"]["identical"] >= 0.999 and d["parity"]["rmse"] <= 1e-3          # the bench line carries its own parity evidence
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
