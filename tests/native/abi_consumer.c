@@ -51,6 +51,19 @@ int main(void)
         }
         printf("rendered paths=%lu rays=%lu lit=%d\n", (unsigned long)stats.paths, (unsigned long)stats.rays, lit);
         if (stats.paths != 16u * 8u * 2u || stats.rays < stats.paths || lit == 0) return 1;
+        /* the device list of one process: two handles on device 0 stand in for two GPUs */
+        {
+            int devices[2] = { 0, 0 };
+            drb_scene* pair[2] = { NULL, NULL };
+            float multi[16 * 8 * 3];
+            drb_stats ms;
+            if (drb_scene_create_multi(hs, devices, 2, 0u, pair) != DRB_OK) { printf("create_multi: %s\n", drb_last_error()); return 1; }
+            opts.flags = DRB_FLAG_DYNAMIC_TILES;
+            if (drb_render_multi(pair, 2, &st, &opts, multi, &ms) != DRB_OK) { printf("render_multi: %s\n", drb_last_error()); return 1; }
+            if (memcmp(multi, accum, sizeof multi) != 0 || ms.rays != stats.rays) { printf("render_multi differs from drb_render\n"); return 1; }
+            printf("multi paths=%lu rays=%lu identical\n", (unsigned long)ms.paths, (unsigned long)ms.rays);
+            drb_scene_free(pair[0]); drb_scene_free(pair[1]);
+        }
     }
     drb_scene_free(scene);
     drb_host_scene_free(hs);

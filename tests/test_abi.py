@@ -104,4 +104,4 @@ def test_header_is_plain_c_and_struct_sizes_agree(tmp_path):
 def test_c_consumer_renders_through_the_abi(tmp_path):
     r = _build_c_consumer(tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rendered paths=256" in r.stdout
+    assert "rendered paths=256" in r.stdout and "multi paths=256" in r.stdout and "identical" in r.stdout
