@@ -45,8 +45,11 @@ constexpr int kTraceThreads = 128;
 #ifndef DRB_TRACE_STEPS
 #define DRB_TRACE_STEPS 2
 #endif
-#ifndef DRB_SORTED_PUSH
-#define DRB_SORTED_PUSH 0
+// Children that are hit besides the nearest one are pushed unsorted for scenes up to this many primitives, far-to-near
+// (five compare-exchanges) above it: the sort costs 2 % on the million-triangle frame and returns 4 % on the
+// 10 M-triangle city, whose rays cross many more boxes before they hit something.
+#ifndef DRB_SORTED_PUSH_FROM
+#define DRB_SORTED_PUSH_FROM (4 << 20)
 #endif
 constexpr int kSteps = DRB_TRACE_STEPS;   // descent steps per lane between two rounds of warp votes
 constexpr uint32_t kInvalidPid = 0xFFFFFFFFu;
@@ -240,6 +243,7 @@ constexpr int kSentinel = (int)0x80000000;     // bottom of every traversal stac
 #ifndef DRB_TRACE_MIN_BLOCKS
 #define DRB_TRACE_MIN_BLOCKS 8
 #endif
+template <bool kSortedPush>
 __global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(DevScene sc, float scene_scale, Queues q, int cur, int refill, int leaf_batch, int step_min,
                                                const uint32_t* __restrict__ order)
 {
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(D
 #undef DRB_CHILD
 #undef DRB_PLANE
             // t_near >= 0, so its bits order like unsigned integers; the two low bits carry the slot
-#if DRB_SORTED_PUSH
+            if constexpr (kSortedPush) {
             // sort the four keys (5 compare-exchanges), push the hits far-to-near, continue with the nearest
             uint32_t a0 = min(k0, k1), a1 = max(k0, k1), a2 = min(k2, k3), a3 = max(k2, k3);
             const uint32_t s0 = min(a0, a2), t1 = max(a0, a2), t2 = min(a1, a3), s3 = max(a1, a3);
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(D
                 node = DRB_LINK(s0);
 #undef DRB_LINK
             }
-#else
+            } else {
             const uint32_t kmin = min(min(k0, k1), min(k2, k3));
             if (kmin == 0xFFFFFFFFu) node = DRB_POP();
             else {
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(kTraceThreads, DRB_TRACE_MIN_BLOCKS) k_trace(D
                 const uint32_t near = kmin & 3u;
                 node = near == 0u ? c0 : (near == 1u ? c1 : (near == 2u ? c2 : c3));
             }
-#endif
+            }
         }
         // a lane that arrives at a leaf stashes it and keeps descending
         if (node < 0 && node != kSentinel && leaf == 0) { leaf = node; node = DRB_POP(); }
@@ -947,10 +951,12 @@ int launch_shape(int device, size_t trace_smem, int* trace_blocks, int* shade_bl
         int sms = 148, per_sm = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (trace_smem > g_facts.max_smem_set[d]) {
-            DRB_CUDA(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
+            DRB_CUDA(cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
+            DRB_CUDA(cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
             g_facts.max_smem_set[d] = trace_smem;
         }
-        DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, kTraceThreads, trace_smem));
+        DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, kTraceThreads, trace_smem));
+        { int other = per_sm; DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, k_trace<true>, kTraceThreads, trace_smem)); per_sm = std::min(per_sm, other); }
         it = g_facts.trace_blocks.emplace(std::make_pair(device, trace_smem), sms * std::max(per_sm, 1)).first;
         DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 128, 0));
         g_facts.shade_blocks[d] = sms * std::max(per_sm, 1);
@@ -1046,6 +1052,15 @@ int g_refill = []() { const char* e = getenv("DOGERAY_B200_REFILL"); int v = e ?
 // stashed leaves are intersected when at least g_leaf_batch lanes hold one, or fewer than g_step_min lanes can descend
 int g_leaf_batch = []() { const char* e = getenv("DOGERAY_B200_LEAF_BATCH"); int v = e ? atoi(e) : 12; return v < 1 ? 1 : v; }();
 int g_step_min = []() { const char* e = getenv("DOGERAY_B200_STEP_MIN"); int v = e ? atoi(e) : 20; return v < 1 ? 1 : v; }();
+
+// the closest-hit kernel for this scene: large scenes push the other hit children far-to-near (see DRB_SORTED_PUSH_FROM)
+void launch_trace(const drb_scene* s, const RenderBuffers* rb, cudaStream_t stream, const DevScene& sc, float scale, const Queues& q, int cur, const uint32_t* order)
+{
+    if (s->nprims >= (int64_t)DRB_SORTED_PUSH_FROM)
+        k_trace<true><<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(sc, scale, q, cur, g_refill, g_leaf_batch, g_step_min, order);
+    else
+        k_trace<false><<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(sc, scale, q, cur, g_refill, g_leaf_batch, g_step_min, order);
+}
 
 
 
@@ -1180,7 +1195,7 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
                 }
             }
             if (stats) { auto e0 = pool.get(), e1 = pool.get(); trace_ev.push_back({ e0, e1 }); DRB_CUDA(cudaEventRecord(e0, stream)); }
-            k_trace<<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(sc, fp.scene_scale, q, cur, g_refill, g_leaf_batch, g_step_min, order);
+            launch_trace(s, rb, stream, sc, fp.scene_scale, q, cur, order);
             if (stats) DRB_CUDA(cudaEventRecord(trace_ev.back().second, stream));
             k_shade<<<std::min<uint32_t>((uint32_t)rb->shade_blocks, (live + 4u * kShadeRays - 1u) / (4u * kShadeRays)), 128, 0, stream>>>(sc, fp, q, cur, b == st->max_depth - 1 ? 1 : 0);
             k_prepare<<<1, 32, 0, stream>>>(q.counters, cur, -1, 0u);
@@ -1521,7 +1536,7 @@ int drb_trace_ids(drb_scene* s, const float* o3, const float* d3, int64_t n, int
     const uint32_t nn = (uint32_t)n;
     k_load_rays<<<(nn + 255) / 256, 256, 0, stream>>>(d_o, d_d, nn, q);
     k_prepare<<<1, 32, 0, stream>>>(q.counters, -1, 0, nn);
-    k_trace<<<rb->trace_blocks, kTraceThreads, rb->trace_smem, stream>>>(dev_scene(s), scene_scale(s), q, 0, g_refill, g_leaf_batch, g_step_min, nullptr);
+    launch_trace(s, rb, stream, dev_scene(s), scene_scale(s), q, 0, nullptr);
     k_store_ids<<<(nn + 255) / 256, 256, 0, stream>>>(q.hit, s->orig_id, nn, d_ids, d_t);
     DRB_CUDA(cudaGetLastError());
     DRB_CUDA(cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
