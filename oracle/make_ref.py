@@ -2,7 +2,7 @@
 """TEST / BASELINE INFRASTRUCTURE -- build the reference itself as the parity oracle.
 
 Nothing of /root/reference is copied into the repository.  This recipe compiles the
-reference's single translation unit, raygpu/kernel.cu, WHERE IT LIES, two ways, and
+reference's single translation unit, raygpu/kernel.cu, WHERE IT LIES, three ways, and
 writes only binaries (and staged sample DATA files) into the git-ignored
 ``oracle/_ref/`` directory, which travels to the GPU box with the gpurun snapshot:
 
@@ -20,6 +20,11 @@ writes only binaries (and staged sample DATA files) into the git-ignored
     ``kernel.cu`` compiled UNMODIFIED by nvcc for sm_100 behind three stub headers
     (``oracle/stubs``) with ``-Dmain=ref_main``, plus the headless driver
     ``ref_gpu_driver.cu``.  This is the "reference kernel rebuilt for sm_100" baseline.
+
+``libdogeray_ref_gpu_count.so``
+    The same build with ONE call inserted in front of ``raycolor``'s ``hit()`` call (kernel.cu:800) that bumps a device
+    counter, so that the GPU baseline's Mrays/s uses the reference's OWN ray count.  The edited stream lives in a
+    temporary file outside the repo for the duration of the compile; this build is never the one that is timed.
 
 ``samples/``
     The reference's sample scenes and textures (DATA, not source), staged so the GPU

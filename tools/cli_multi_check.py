@@ -1,6 +1,6 @@
 """The in-process multi-GPU path (drb_scene_create_multi + drb_render_multi) on a box with several GPUs:
 
-    python tools/cli_multi_check.py [spp] [grid1m|city10m]
+    python tools/cli_multi_check.py [spp] [grid1m|city10m|mats]
 
   * the CLI at --gpus 1/2/4/8 (static tiles, --dynamic, --shard samples): byte-identical BMPs for the tile modes, wall
     clock and the device time the CLI prints;
@@ -23,11 +23,17 @@ spp = sys.argv[1] if len(sys.argv) > 1 else "64"
 which = sys.argv[2] if len(sys.argv) > 2 else "grid1m"
 cli = os.path.join(os.path.dirname(drb.__file__), "dogeray-b200")
 d = tempfile.mkdtemp(prefix="drb_cli_")
-objs, st = synth.city_scene() if which == "city10m" else synth.instanced_grid_scene()
+tex = []
+if which == "city10m":
+    objs, st = synth.city_scene()
+elif which == "mats":                                    # BASELINE config 4 stand-in: every material class, textures, environment map
+    objs, st, tex = synth.materials_scene(synth.write_test_textures(d))
+else:
+    objs, st = synth.instanced_grid_scene()
 res = "%dx%d" % (st.width, st.height)
 ndev = drb.device_count()
 out, rows = {}, []
-use_cli = which != "city10m"            # the 10 M-triangle scene is 3.3 GB of text: it goes through the library only
+use_cli = which == "grid1m"             # the 10 M-triangle scene is 3.3 GB of text: it and the material scene go through the library only
 if use_cli:
     drb.write_rts(os.path.join(d, "scene.rts"), st, objs)
 for n in (1, 2, 4, 8):
@@ -51,7 +57,7 @@ for n in (1, 2, 4, 8):
         if mode != "samples":
             assert out[(n, mode)] == out[(1, "tiles")], "image differs from the 1-GPU image"
 # static imbalance through the library
-hs = drb.HostScene.load(os.path.join(d, "scene.rts"), d, cache=True) if use_cli else drb.HostScene.from_objects(objs, st)
+hs = drb.HostScene.load(os.path.join(d, "scene.rts"), d, cache=True) if use_cli else drb.HostScene.from_objects(objs, st, tex)
 one = None
 for n in (1, 2, 4, 8):
     if n > ndev:
