@@ -1177,8 +1177,10 @@ int render_core(drb_scene* s, const drb_settings* st, const drb_opts* opts, int 
         uint32_t live = nslots;
         for (int b = 0; b < st->max_depth; ++b) {
             const uint32_t* order = nullptr;
-            if (b > 0) {
-                // the queue size decides whether the bounce is worth reordering, and ends the batch early
+            // The queue size ends the batch early and sizes the shade grid.  Reading it back drains the stream, so it is read
+            // every fourth bounce only (queues never grow from one bounce to the next: the last value read is an upper bound);
+            // the opt-in reordering needs it every bounce.
+            if (b > 0 && (g_sort_min > 0 || (b & 3) == 0)) {
                 DRB_CUDA(cudaMemcpyAsync(&live, q.counters + cur, sizeof live, cudaMemcpyDeviceToHost, stream));
                 DRB_CUDA(cudaStreamSynchronize(stream));
                 if (live == 0) break;
