@@ -21,7 +21,9 @@ struct Philox4 { uint32_t v[4]; };
 
 DRB_HD Philox4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
 {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int r = 0; r < 10; ++r) {
 #ifdef __CUDA_ARCH__
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -62,7 +64,8 @@ struct PathRng {
     }
     static DRB_HD float to_uniform(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
     DRB_HD float uniform() { return to_uniform(word()); }
-    // The next three words at once (draws n, n+1, n+2).  Same stream as three word() calls, but the block function
+    // The next three words at once (draws n, n+1, n+2) -- the definition of what one unit-sphere attempt consumes; k_shade's
+    // pooled sampling stage (render.cu) inlines exactly this selection.  Same stream as three word() calls, but the block function
     // sits at ONE call site: lanes of a warp whose streams are at different phases (n & 3) generate their next block
     // together instead of one phase after the other, which is what three word() calls compile to.
     DRB_HD void words3(uint32_t& a, uint32_t& b, uint32_t& c)

@@ -119,17 +119,8 @@ DRB_D bool slot_to_pixel(const FrameParams& fp, uint32_t slot, int& x, int& y, u
 // (kernel.cu:200-203, 641); that is decided by d = dot(p, p) alone, without the square root: for d >= 1 the correctly
 // rounded root is >= 1 and so is its square; for d < 1 the root rounds to at most 1 - 2^-24 (sqrt(1 - 2^-24) lies below
 // the midpoint 1 - 2^-25), whose square, under powf's sub-ulp error as under a float multiply, stays below 1.
-DRB_D f3 random_in_unit_sphere(PathRng& rng)
-{
-    for (;;) {
-        uint32_t wc, wb, wa;
-        rng.words3(wc, wb, wa);
-        const float c = PathRng::to_uniform(wc), b = PathRng::to_uniform(wb), a = PathRng::to_uniform(wa);
-        const f3 p = mk3(a * 2.0f - 1.0f, b * 2.0f - 1.0f, c * 2.0f - 1.0f);
-        if (dot(p, p) >= 1.0f) continue;                 // == the reference's pow(getLength(p), 2) >= 1 (see above)
-        return p;
-    }
-}
+// (random_in_unit_sphere itself, kernel.cu:640-647, lives in k_shade's pooled sampling stage: one lane per request with
+// refill, then teams of lanes for the last requests; both consume words draws, draws + 1, draws + 2 per attempt.)
 DRB_D f3 random_in_unit_disk(PathRng& rng)
 {
     for (;;) {
@@ -631,7 +622,7 @@ __global__ void __launch_bounds__(128, DRB_SHADE_MIN_BLOCKS) k_shade(DevScene sc
         if (nreq > 0) {
             int next = 32;                                      // requests [0, 32) start on the lanes; the rest is handed out as lanes finish
             int mine = -1;
-            uint32_t x = 0, y = 0, smp = 0, draws = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            uint32_t x = 0, y = 0, smp = 0, draws = 0, w1 = 0, w2 = 0, w3 = 0;    // w1..w3: the block's words not consumed yet (word 0 always is)
             bool regen = false;
 #define DRB_TAKE(r_) do { mine = (int)req[(r_)]; const uint32_t xy_ = __float_as_uint(rec[REC_XY][mine]), pid_ = __float_as_uint(rec[REC_PID][mine]); \
                           x = xy_ & 0xFFFFu; y = xy_ >> 16; smp = fp.sample_base + (pid_ >> 5) % fp.samples; \
@@ -646,13 +637,13 @@ __global__ void __launch_bounds__(128, DRB_SHADE_MIN_BLOCKS) k_shade(DevScene sc
                         n0 = p.v[0]; n1 = p.v[1]; n2 = p.v[2]; n3 = p.v[3];
                     }
                     bool attempt = true;
-                    if (regen) { w0 = n0; w1 = n1; w2 = n2; w3 = n3; regen = false; attempt = (ph == 1u); }
+                    if (regen) { w1 = n1; w2 = n2; w3 = n3; regen = false; attempt = (ph == 1u); }
                     if (attempt) {
-                        // words draws, draws + 1, draws + 2 (PathRng::words3); the FIRST lands in the LAST component (see random_in_unit_sphere)
+                        // words draws, draws + 1, draws + 2 (PathRng::words3); the FIRST lands in the LAST component (see the sampling helpers)
                         const uint32_t wc = ph == 0u ? n0 : (ph == 1u ? w1 : (ph == 2u ? w2 : w3));
                         const uint32_t wb = ph == 0u ? n1 : (ph == 1u ? w2 : (ph == 2u ? w3 : n0));
                         const uint32_t wa = ph == 0u ? n2 : (ph == 1u ? w3 : (ph == 2u ? n0 : n1));
-                        if (ph != 1u) { w0 = n0; w1 = n1; w2 = n2; w3 = n3; }
+                        if (ph != 1u) { w1 = n1; w2 = n2; w3 = n3; }
                         draws += 3u;
                         const f3 p = mk3(PathRng::to_uniform(wa) * 2.0f - 1.0f, PathRng::to_uniform(wb) * 2.0f - 1.0f, PathRng::to_uniform(wc) * 2.0f - 1.0f);
                         if (!(dot(p, p) >= 1.0f)) {
